@@ -1,0 +1,169 @@
+/*
+ * seqpurge_b200.h -- C ABI of the B200 SeqPurge trimming engine (libseqpurge_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of imgag/ngs-bits that this repository accelerates:
+ * the per-read-pair body of AnalysisWorker::run (src/SeqPurge/AnalysisWorker.cpp:97-448 in the reference).
+ * The reference has no FFI for this path -- the seam is the C++ class boundary
+ *     ThreadCoordinator::analyze(int i)          src/SeqPurge/ThreadCoordinator.cpp:92-98
+ *       -> new AnalysisWorker(job, params, stats, ecstats); run()   src/SeqPurge/AnalysisWorker.h:15-17
+ * so every entry point below names the piece of that seam it replaces. INTEGRATION.md shows the
+ * GpuAnalysisWorker a maintainer adds under src/SeqPurge to bind them.
+ *
+ * Conventions: plain pointers and sizes only, no C++/Qt/torch types, no exceptions. Every call returns
+ * SPG_OK (0) or a negative SPG_ERR_* code; spg_last_error() gives the text (the shim turns it into
+ * `emit error(i, msg)`, which the reference maps to THROW + exit(1), ThreadCoordinator.cpp:108-111).
+ * There is no CPU fallback behind this ABI: without a CUDA device spg_create fails with SPG_ERR_CUDA.
+ */
+#ifndef SEQPURGE_B200_H
+#define SEQPURGE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPG_OK 0
+#define SPG_ERR_PARAM (-1) /* invalid argument / parameter combination */
+#define SPG_ERR_CUDA (-2)  /* CUDA runtime error or no device */
+#define SPG_ERR_STATE (-3) /* slot used out of protocol (submit twice, wait without submit, ...) */
+#define SPG_ERR_NOMEM (-4)
+
+#define SPG_MAXLEN 1000 /* MAXLEN, src/SeqPurge/Auxilary.h:12: reads must be shorter than this */
+
+/* spg_result.flags */
+#define SPG_F_INSERT 0x01u  /* insert match: both reads cut to len2-best_offset   (AnalysisWorker.cpp:269-302) */
+#define SPG_F_ADAPTER 0x02u /* adapter-only hit on at least one read               (AnalysisWorker.cpp:410-426) */
+#define SPG_F_Q1 0x04u      /* read 1 lost bases to trimQuality                    (AnalysisWorker.cpp:432) */
+#define SPG_F_Q2 0x08u      /* read 2 lost bases to trimQuality                    (AnalysisWorker.cpp:433) */
+#define SPG_F_N1 0x10u      /* read 1 lost bases to trimN                          (AnalysisWorker.cpp:439) */
+#define SPG_F_N2 0x20u      /* read 2 lost bases to trimN                          (AnalysisWorker.cpp:440) */
+
+/* spg_result.status: per-pair conditions on which the reference throws */
+#define SPG_PAIR_OK 0
+#define SPG_PAIR_BAD_BASE_R2 1 /* byte outside ACGTN in read 2: Sequence::complement throws (src/cppNGS/Sequence.cpp:46-71) */
+#define SPG_PAIR_TOO_LONG 2    /* max(len1,len2) >= MAXLEN: ArgumentException (AnalysisWorker.cpp:131-134) */
+#define SPG_PAIR_BAD_BASE_EC 3 /* -ec had to complement a non-ACGTN byte of read 1 (AnalysisWorker.cpp:50, Sequence.cpp:103-112) */
+
+/* Run constants. Replaces the fields of TrimmingParameters that AnalysisWorker reads
+   (src/SeqPurge/Auxilary.h:100-133; defaults src/SeqPurge/main.cpp:25-43). a_size = min(20,|a1|,|a2|) is derived
+   inside (main.cpp:71). */
+typedef struct spg_params
+{
+	const char* a1;      /* forward adapter, >= 15 bytes (main.cpp:68) */
+	int32_t a1_len;
+	const char* a2;      /* reverse adapter, >= 15 bytes (main.cpp:70) */
+	int32_t a2_len;
+	int32_t adapter_overlap; /* 10 (Auxilary.h:103); 1..32 */
+	double match_perc;   /* -match_perc, 80.0 */
+	double mep;          /* -mep, 1e-6 */
+	int32_t qcut;        /* -qcut 15 (0 disables) */
+	int32_t qwin;        /* -qwin 5 */
+	int32_t qoff;        /* -qoff 33 */
+	int32_t ncut;        /* -ncut 7 (0 disables) */
+	int32_t ec;          /* -ec: error-correct insert-hit pairs; edited rows are returned in the slot */
+} spg_params;
+
+/* Per-pair output: everything OutputWorker / FastqWriter / TrimmingStatistics need (OutputWorker.cpp:36-77). 8 bytes. */
+typedef struct spg_result
+{
+	uint16_t len1;       /* read 1: keep bases/qualities [0,len1) */
+	uint16_t len2;       /* read 2: keep bases/qualities [0,len2) */
+	int16_t best_offset; /* insert-match offset (for the adapter-consensus counters, AnalysisWorker.cpp:279-290), -1 if none */
+	uint8_t flags;       /* SPG_F_* */
+	uint8_t status;      /* SPG_PAIR_* ; when != 0 the other fields are 0 / -1 */
+} spg_result;
+
+/* One slot == one AnalysisJob of the reference's job pool (Auxilary.h:23-66): pinned host SoA the caller fills.
+   Row r of each byte plane starts at r*stride; bytes beyond the read length are ignored. */
+typedef struct spg_slot_view
+{
+	uint8_t* bases1; /* FastqEntry::bases of job.r1[r]      */
+	uint8_t* quals1; /* FastqEntry::qualities of job.r1[r]  */
+	uint8_t* bases2;
+	uint8_t* quals2;
+	uint16_t* len1;  /* bases1/quals1 row length (the reference assumes |bases|==|qualities|) */
+	uint16_t* len2;
+	int32_t stride;    /* bytes per row, multiple of 16, >= max_len */
+	int32_t max_pairs; /* capacity (the reference's -block_size) */
+} spg_slot_view;
+
+/* Error-correction histograms, replaces ErrorCorrectionStatistics (Auxilary.h:224-236) */
+typedef struct spg_ec_stats
+{
+	int64_t mismatch_r1[SPG_MAXLEN];
+	int64_t mismatch_r2[SPG_MAXLEN];
+	int64_t errors_per_read[SPG_MAXLEN];
+} spg_ec_stats;
+
+typedef struct spg_ctx spg_ctx;
+
+/* Replaces: main.cpp:92 (precalculateFactorials), ThreadCoordinator.cpp:40-48 (analysis pool + job pool allocation).
+   Builds the decision tables (match-probability ranks etc.) with the host's libm exactly as
+   BasicStatistics::matchProbability does, uploads them to every device, allocates n_slots pinned host slots and the
+   matching device buffers. Slot s runs on device_ids[s % n_devices] (host-side round robin, no collective).
+   max_len: longest read the caller will submit (<= 999). n_slots may be 0 (only spg_trim_device is used). */
+int spg_create(spg_ctx** ctx, const spg_params* params, const int* device_ids, int n_devices, int n_slots, int max_pairs, int max_len);
+
+/* Replaces: AnalysisJob storage (Auxilary.h:37-39). Pointers stay valid until spg_destroy. */
+int spg_slot_buffers(spg_ctx* ctx, int slot, spg_slot_view* view);
+
+/* Replaces: thread_pool_analyze_.start(worker) (ThreadCoordinator.cpp:97). Asynchronous: H2D copy of the first n_pairs
+   rows, the trimming kernel, D2H of the results (and of the edited rows with -ec) are queued on the slot's device stream. */
+int spg_submit(spg_ctx* ctx, int slot, int n_pairs);
+
+/* Replaces: AnalysisWorker's done(int)/error(int,QString) signals (AnalysisWorker.h:19-21). Blocks until the slot's
+   work has finished; *results points at n_pairs records in pinned host memory, valid until the slot is resubmitted. */
+int spg_wait(spg_ctx* ctx, int slot, const spg_result** results);
+
+/* Device-resident form of the same operation (no copies): all pointers are device pointers on device_ids[device_index],
+   16-byte aligned; len arrays must be readable up to a multiple of 8 entries; stride a multiple of 16.
+   cuda_stream is a cudaStream_t (NULL = default stream). With -ec the row planes are edited in place. */
+int spg_trim_device(spg_ctx* ctx, int device_index, void* bases1, void* quals1, void* bases2, void* quals2, const uint16_t* len1, const uint16_t* len2,
+                    int stride, int64_t n_pairs, spg_result* results, void* cuda_stream);
+
+/* Accumulated -ec histograms of everything waited for so far (Auxilary.h:224-236). */
+int spg_ec_stats_get(spg_ctx* ctx, spg_ec_stats* out);
+
+/* Text of the last error on this context (or of the last failed spg_create when ctx is NULL). */
+const char* spg_last_error(spg_ctx* ctx);
+
+/* Replaces: ~ThreadCoordinator. Waits for queued work, frees everything. */
+void spg_destroy(spg_ctx* ctx);
+
+/* ---- tuning / introspection (not part of the reference seam) ------------------------------------------------------------ */
+
+#define SPG_OPT_FORCE_BYTEWISE 1 /* value 1: route every pair through the byte-wise kernel path (cross-check of the bit-plane path) */
+#define SPG_OPT_GRID_CTAS_PER_SM 2
+int spg_set_option(spg_ctx* ctx, int option, int value);
+
+/* number of kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
+int64_t spg_launch_count(spg_ctx* ctx);
+
+/* ---- synthetic read pairs, generated on the device (bench / tests) --------------------------------------- */
+typedef struct spg_synth_config
+{
+	int32_t read_len;      /* L */
+	float insert_mean;     /* mu */
+	float insert_sd;       /* sigma */
+	int32_t insert_min;    /* clip */
+	int32_t insert_max;
+	float error_rate;      /* i.i.d. substitution rate */
+	float n_rate;          /* per-base N rate */
+	float lowq_tail_mean;  /* mean length of the low-quality 3' tail ('#'), 0 = none */
+	float n_run_rate;      /* fraction of reads that get a run of >= 7 N */
+	int32_t binned_quals;  /* 1: NovaSeq-like binned qualities F : , # */
+	uint64_t seed;
+	const char* a1;        /* adapters appended after the insert (33 bytes used at most; NULL = Illumina defaults) */
+	const char* a2;
+} spg_synth_config;
+
+/* Fills device row planes for pairs [first_pair, first_pair+n_pairs) of the stream defined by cfg (counter based:
+   any slice can be regenerated). Pointers as in spg_trim_device. */
+int spg_synth_device(int device_id, const spg_synth_config* cfg, int64_t first_pair, int64_t n_pairs, void* bases1, void* quals1, void* bases2, void* quals2,
+                     uint16_t* len1, uint16_t* len2, int stride, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,627 @@
+// spg_engine.cu -- host side of libseqpurge_b200.so: the C ABI of include/seqpurge_b200.h.
+//
+// Builds the integer decision tables on the host (with the host's libm, evaluating the same expressions as
+// BasicStatistics::matchProbability / AnalysisWorker::run of the reference, src/cppCORE/BasicStatistics.cpp:281-307,
+// src/SeqPurge/AnalysisWorker.cpp:170,178-179,246-259,346-348), owns the pinned slots and the per-device buffers and
+// streams, and launches spg::trim_kernel. No CPU implementation of the trimming itself exists in this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "spg_kernel.cuh"
+
+namespace
+{
+
+std::string g_create_error;
+
+// ---- decision tables ---------------------------------------------------------------------------------------------------------------------
+struct HostTables
+{
+	std::vector<uint16_t> mmin;    // [1000]
+	std::vector<uint16_t> ranktab; // [171*171]
+	std::vector<double> psmall;    // [(ao+1)^2]
+	uint32_t passA[21];
+	int qthr;
+};
+
+struct Factorials
+{
+	std::vector<double> f; // k! while it fits a double: 0..170
+	Factorials()
+	{
+		double v = 1.0;
+		int i = 0;
+		while (std::isfinite(v))
+		{
+			f.push_back(v);
+			++i;
+			v *= i;
+		}
+	}
+};
+const Factorials& factorials()
+{
+	static Factorials F;
+	return F;
+}
+
+// P(X >= n), X ~ Binomial(count, p), evaluated term by term in increasing i exactly like the reference does
+double match_probability(double p, int n, int count)
+{
+	const std::vector<double>& f = factorials().f;
+	int mismatches = count - n;
+	while (count >= (int)f.size())
+	{
+		n /= 2;
+		mismatches /= 2;
+		count = n + mismatches;
+	}
+	double output = 0.0;
+	for (int i = n; i <= count; ++i)
+	{
+		double q = std::pow(1.0 - p, (double)(count - i)) * std::pow(p, (double)i) * f[count] / f[i] / f[count - i];
+		output += q;
+	}
+	return output;
+}
+
+bool build_tables(const spg_params& p, int a_size, HostTables& t, std::string& err)
+{
+	if ((int)factorials().f.size() != spg::kRankDim)
+	{
+		err = "unexpected factorial cache size";
+		return false;
+	}
+	// minimum matches per number of compared bases T: smallest m with !(100.0*m/T < match_perc)
+	t.mmin.assign(SPG_MAXLEN, 0xFFFF);
+	for (int T = 1; T < SPG_MAXLEN; ++T)
+	{
+		for (int m = 0; m <= T; ++m)
+		{
+			if (!(100.0 * m / T < p.match_perc))
+			{
+				t.mmin[T] = (uint16_t)m;
+				break;
+			}
+		}
+	}
+	// dense ranks of the probabilities that pass -mep
+	std::vector<double> ps;
+	std::vector<double> cell((size_t)spg::kRankDim * spg::kRankDim, std::numeric_limits<double>::quiet_NaN());
+	for (int count = 0; count < spg::kRankDim; ++count)
+	{
+		for (int n = 0; n <= count; ++n)
+		{
+			double v = match_probability(0.25, n, count);
+			if (!std::isfinite(v))
+			{
+				err = "match probability is not finite";
+				return false;
+			}
+			cell[(size_t)count * spg::kRankDim + n] = v;
+			if (!(v > p.mep)) ps.push_back(v);
+		}
+	}
+	std::sort(ps.begin(), ps.end());
+	ps.erase(std::unique(ps.begin(), ps.end()), ps.end());
+	if (ps.size() >= 0xFFFF)
+	{
+		err = "too many distinct probabilities";
+		return false;
+	}
+	t.ranktab.assign((size_t)spg::kRankDim * spg::kRankDim, 0xFFFF);
+	for (int count = 0; count < spg::kRankDim; ++count)
+	{
+		for (int n = 0; n <= count; ++n)
+		{
+			double v = cell[(size_t)count * spg::kRankDim + n];
+			if (v > p.mep) continue;
+			t.ranktab[(size_t)count * spg::kRankDim + n] = (uint16_t)(std::lower_bound(ps.begin(), ps.end(), v) - ps.begin());
+		}
+	}
+	// probabilities of the short adapter fragments of the presence check
+	const int ao = p.adapter_overlap;
+	t.psmall.assign((size_t)(ao + 1) * (ao + 1), 1.0);
+	for (int count = 0; count <= ao; ++count)
+		for (int n = 0; n <= count; ++n) t.psmall[(size_t)count * (ao + 1) + n] = match_probability(0.25, n, count);
+	// adapter-only scans: pass bit per (compared bases T, matches m); T=0 gives 0/0 = NaN, which is not "< match_perc"
+	for (int T = 0; T <= 20; ++T)
+	{
+		t.passA[T] = 0;
+		for (int m = 0; m <= T && T <= a_size; ++m)
+		{
+			int mm = T - m;
+			if (100.0 * m / (m + mm) < p.match_perc) continue;
+			if (match_probability(0.25, m, m + mm) > p.mep) continue;
+			t.passA[T] |= 1u << m;
+		}
+	}
+	// quality window: smallest integer sum s with (double)s/window >= cutoff (FastqFileStream.cpp:69)
+	{
+		long long s = (long long)p.qcut * p.qwin - 8;
+		while (!((double)s / p.qwin >= p.qcut)) ++s;
+		t.qthr = (int)s;
+	}
+	return true;
+}
+
+void adapter_planes(const char* a, int a_size, uint32_t& h, uint32_t& l, uint32_t& n)
+{
+	h = l = n = 0;
+	for (int i = 0; i < a_size; ++i)
+	{
+		unsigned c = (unsigned char)a[i];
+		if (c & 4u) h |= 1u << i;
+		if (c & 2u) l |= 1u << i;
+		if (c == 'N') n |= 1u << i;
+	}
+}
+
+bool all_acgtn(const char* a, int n)
+{
+	for (int i = 0; i < n; ++i)
+	{
+		char c = a[i];
+		if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') return false;
+	}
+	return true;
+}
+
+// ---- context ---------------------------------------------------------------------------------------------------------------------------------
+struct Device
+{
+	int id = -1;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	uint16_t* d_mmin = nullptr;
+	uint16_t* d_rank = nullptr;
+	double* d_psmall = nullptr;
+	unsigned long long* d_ec = nullptr; // 3 * SPG_MAXLEN
+	int occ[4] = {0, 0, 0, 0};          // resident CTAs per SM for NW = 0,5,8,10 at the configured smem size
+};
+
+enum SlotState
+{
+	SLOT_IDLE = 0,
+	SLOT_SUBMITTED = 1
+};
+
+struct Slot
+{
+	int dev = 0;
+	uint8_t* h_block = nullptr; // pinned: b1|q1|b2|q2|len1|len2
+	uint8_t* d_block = nullptr;
+	spg_result* h_res = nullptr;
+	spg_result* d_res = nullptr;
+	cudaEvent_t done = nullptr;
+	int state = SLOT_IDLE;
+	int n = 0;
+};
+
+} // namespace
+
+struct spg_ctx
+{
+	spg_params params;
+	std::string a1, a2;
+	int a_size = 0;
+	bool adapters_plain = true; // adapters consist of ACGTN only
+	HostTables tables;
+	std::vector<Device> devs;
+	std::vector<Slot> slots;
+	int max_pairs = 0, max_len = 0, stride = 0;
+	size_t plane_bytes = 0, len_bytes = 0, block_bytes = 0;
+	std::string err;
+	std::mutex mu;
+	int force_bytewise = 0;
+	int ctas_per_sm = 0; // 0 = occupancy
+	long long launches = 0;
+	spg_ec_stats ec_total;
+};
+
+namespace
+{
+
+int fail(spg_ctx* ctx, int code, const std::string& msg)
+{
+	if (ctx)
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		ctx->err = msg;
+	}
+	else g_create_error = msg;
+	return code;
+}
+#define SPG_CUDA(ctx, call)                                                                                           \
+	do                                                                                                                \
+	{                                                                                                                 \
+		cudaError_t e_ = (call);                                                                                      \
+		if (e_ != cudaSuccess) return fail(ctx, SPG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+	} while (0)
+
+int nw_for_stride(int stride) { return stride <= 160 ? 5 : stride <= 256 ? 8 : stride <= 320 ? 10 : 0; }
+int nw_index(int nw) { return nw == 5 ? 1 : nw == 8 ? 2 : nw == 10 ? 3 : 0; }
+
+void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
+{
+	int tp = (int)(24576 / (4 * (size_t)stride + 4)) / 8 * 8;
+	if (tp < 8) tp = 8;
+	if (tp > 64) tp = 64;
+	tile_pairs = tp;
+	stages = 3;
+	smem = (size_t)stages * (4 * (size_t)tp * stride + 4 * (size_t)tp);
+}
+
+template <int NW>
+cudaError_t launch_nw(const spg::KArgs& a, int grid, size_t smem, cudaStream_t stream)
+{
+	static thread_local size_t configured[64] = {0};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 64 && configured[dev] < smem)
+	{
+		cudaError_t e = cudaFuncSetAttribute(spg::trim_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		configured[dev] = smem;
+	}
+	spg::trim_kernel<NW><<<grid, spg::kThreads, smem, stream>>>(a);
+	return cudaGetLastError();
+}
+
+template <int NW>
+int occupancy_nw(size_t smem)
+{
+	cudaFuncSetAttribute(spg::trim_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	int n = 0;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::trim_kernel<NW>, spg::kThreads, smem) != cudaSuccess) n = 1;
+	return n < 1 ? 1 : n;
+}
+
+int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride, long long n,
+                spg_result* out, cudaStream_t stream)
+{
+	if (n <= 0) return SPG_OK;
+	spg::KArgs a;
+	memset(&a, 0, sizeof(a));
+	a.b1 = b1;
+	a.q1 = q1;
+	a.b2 = b2;
+	a.q2 = q2;
+	a.len1 = len1;
+	a.len2 = len2;
+	a.out = out;
+	a.n_pairs = n;
+	a.stride = stride;
+	size_t smem;
+	tile_geometry(stride, a.tile_pairs, a.stages, smem);
+	a.mmin = d.d_mmin;
+	a.ranktab = d.d_rank;
+	a.psmall = d.d_psmall;
+	a.ec_m1 = d.d_ec;
+	a.ec_m2 = d.d_ec + SPG_MAXLEN;
+	a.ec_epr = d.d_ec + 2 * SPG_MAXLEN;
+	const spg_params& p = ctx->params;
+	a.mep = p.mep;
+	a.a_size = ctx->a_size;
+	a.ao = p.adapter_overlap;
+	a.qcut = p.qcut;
+	a.qwin = p.qwin;
+	a.qoff = p.qoff;
+	a.qthr = ctx->tables.qthr;
+	a.ncut = p.ncut;
+	a.ec = p.ec;
+	a.force_bytewise = (ctx->force_bytewise || !ctx->adapters_plain) ? 1 : 0;
+	adapter_planes(ctx->a1.data(), ctx->a_size, a.a1h, a.a1l, a.a1n);
+	adapter_planes(ctx->a2.data(), ctx->a_size, a.a2h, a.a2l, a.a2n);
+	memcpy(a.passA, ctx->tables.passA, sizeof(a.passA));
+	memset(a.a1, 'N', sizeof(a.a1)); // never read beyond the adapter length: a_size, adapter_overlap <= min(|a1|,|a2|,32)
+	memset(a.a2, 'N', sizeof(a.a2));
+	memcpy(a.a1, ctx->a1.data(), std::min<size_t>(32, ctx->a1.size()));
+	memcpy(a.a2, ctx->a2.data(), std::min<size_t>(32, ctx->a2.size()));
+
+	const int nw = nw_for_stride(stride);
+	int& occ = d.occ[nw_index(nw)];
+	if (occ == 0)
+	{
+		switch (nw)
+		{
+			case 5: occ = occupancy_nw<5>(smem); break;
+			case 8: occ = occupancy_nw<8>(smem); break;
+			case 10: occ = occupancy_nw<10>(smem); break;
+			default: occ = occupancy_nw<0>(smem); break;
+		}
+	}
+	const long long n_tiles = (n + a.tile_pairs - 1) / a.tile_pairs;
+	const int per_sm = ctx->ctas_per_sm > 0 ? std::min(ctx->ctas_per_sm, occ) : occ;
+	const int grid = (int)std::min<long long>(n_tiles, (long long)d.sm_count * per_sm);
+	cudaError_t e;
+	switch (nw)
+	{
+		case 5: e = launch_nw<5>(a, grid, smem, stream); break;
+		case 8: e = launch_nw<8>(a, grid, smem, stream); break;
+		case 10: e = launch_nw<10>(a, grid, smem, stream); break;
+		default: e = launch_nw<0>(a, grid, smem, stream); break;
+	}
+	if (e != cudaSuccess) return fail(ctx, SPG_ERR_CUDA, std::string("trim_kernel launch: ") + cudaGetErrorString(e));
+	{
+		std::lock_guard<std::mutex> g(ctx->mu);
+		++ctx->launches;
+	}
+	return SPG_OK;
+}
+
+} // namespace
+
+extern "C"
+{
+
+int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, int n_devices, int n_slots, int max_pairs, int max_len)
+{
+	if (!out || !params) return fail(nullptr, SPG_ERR_PARAM, "null argument");
+	*out = nullptr;
+	if (!params->a1 || !params->a2 || params->a1_len < 15 || params->a2_len < 15)
+		return fail(nullptr, SPG_ERR_PARAM, "adapters must have at least 15 bases"); // main.cpp:68,70
+	if (params->adapter_overlap < 1 || params->adapter_overlap > 32 || params->adapter_overlap > std::min(params->a1_len, params->a2_len))
+		return fail(nullptr, SPG_ERR_PARAM, "adapter_overlap out of range");
+	if (params->qcut > 0 && (params->qwin < 1 || params->qwin >= SPG_MAXLEN)) return fail(nullptr, SPG_ERR_PARAM, "qwin out of range");
+	if (params->ncut < 0 || params->qcut < 0) return fail(nullptr, SPG_ERR_PARAM, "negative qcut/ncut");
+	if (!(params->match_perc == params->match_perc) || !(params->mep == params->mep)) return fail(nullptr, SPG_ERR_PARAM, "match_perc/mep is NaN");
+	if (n_devices < 1 || !device_ids) return fail(nullptr, SPG_ERR_PARAM, "at least one device is required");
+	if (n_slots < 0 || (n_slots > 0 && (max_pairs < 1 || max_len < 1))) return fail(nullptr, SPG_ERR_PARAM, "invalid slot geometry");
+	if (max_len >= SPG_MAXLEN) return fail(nullptr, SPG_ERR_PARAM, "max_len must be below 1000 (MAXLEN of the reference)");
+
+	int dev_count = 0;
+	cudaError_t ce = cudaGetDeviceCount(&dev_count);
+	if (ce != cudaSuccess || dev_count == 0)
+		return fail(nullptr, SPG_ERR_CUDA, std::string("no CUDA device available (this library has no CPU path): ") + cudaGetErrorString(ce));
+	for (int i = 0; i < n_devices; ++i)
+		if (device_ids[i] < 0 || device_ids[i] >= dev_count) return fail(nullptr, SPG_ERR_PARAM, "device id out of range");
+
+	spg_ctx* ctx = new (std::nothrow) spg_ctx();
+	if (!ctx) return fail(nullptr, SPG_ERR_NOMEM, "out of memory");
+	ctx->params = *params;
+	ctx->a1.assign(params->a1, (size_t)params->a1_len);
+	ctx->a2.assign(params->a2, (size_t)params->a2_len);
+	ctx->params.a1 = ctx->a1.data();
+	ctx->params.a2 = ctx->a2.data();
+	ctx->a_size = std::min(20, std::min(params->a1_len, params->a2_len)); // main.cpp:71
+	ctx->adapters_plain = all_acgtn(ctx->a1.data(), std::min(32, params->a1_len)) && all_acgtn(ctx->a2.data(), std::min(32, params->a2_len));
+	memset(&ctx->ec_total, 0, sizeof(ctx->ec_total));
+	std::string err;
+	if (!build_tables(ctx->params, ctx->a_size, ctx->tables, err))
+	{
+		delete ctx;
+		return fail(nullptr, SPG_ERR_PARAM, err);
+	}
+	ctx->max_pairs = max_pairs;
+	ctx->max_len = max_len;
+	ctx->stride = n_slots > 0 ? (max_len + 15) / 16 * 16 : 0;
+	const int cap = (max_pairs + 7) / 8 * 8;
+	ctx->plane_bytes = (size_t)cap * ctx->stride;
+	ctx->len_bytes = (size_t)cap * sizeof(uint16_t);
+	ctx->block_bytes = 4 * ctx->plane_bytes + 2 * ctx->len_bytes;
+
+#define CREATE_CUDA(call)                                                                     \
+	do                                                                                        \
+	{                                                                                         \
+		cudaError_t e_ = (call);                                                              \
+		if (e_ != cudaSuccess)                                                                \
+		{                                                                                     \
+			std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_);              \
+			spg_destroy(ctx);                                                                 \
+			return fail(nullptr, SPG_ERR_CUDA, m_);                                           \
+		}                                                                                     \
+	} while (0)
+
+	ctx->devs.resize((size_t)n_devices);
+	for (int i = 0; i < n_devices; ++i)
+	{
+		Device& d = ctx->devs[(size_t)i];
+		d.id = device_ids[i];
+		CREATE_CUDA(cudaSetDevice(d.id));
+		cudaDeviceProp prop;
+		CREATE_CUDA(cudaGetDeviceProperties(&prop, d.id));
+		if (prop.major < 10)
+		{
+			spg_destroy(ctx);
+			return fail(nullptr, SPG_ERR_CUDA, "device is not sm_100 (this library is built for B200 only)");
+		}
+		d.sm_count = prop.multiProcessorCount;
+		CREATE_CUDA(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+		CREATE_CUDA(cudaMalloc(&d.d_mmin, ctx->tables.mmin.size() * sizeof(uint16_t)));
+		CREATE_CUDA(cudaMalloc(&d.d_rank, ctx->tables.ranktab.size() * sizeof(uint16_t)));
+		CREATE_CUDA(cudaMalloc(&d.d_psmall, ctx->tables.psmall.size() * sizeof(double)));
+		CREATE_CUDA(cudaMalloc(&d.d_ec, 3 * SPG_MAXLEN * sizeof(unsigned long long)));
+		CREATE_CUDA(cudaMemcpy(d.d_mmin, ctx->tables.mmin.data(), ctx->tables.mmin.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+		CREATE_CUDA(cudaMemcpy(d.d_rank, ctx->tables.ranktab.data(), ctx->tables.ranktab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+		CREATE_CUDA(cudaMemcpy(d.d_psmall, ctx->tables.psmall.data(), ctx->tables.psmall.size() * sizeof(double), cudaMemcpyHostToDevice));
+		CREATE_CUDA(cudaMemset(d.d_ec, 0, 3 * SPG_MAXLEN * sizeof(unsigned long long)));
+	}
+	ctx->slots.resize((size_t)n_slots);
+	for (int s = 0; s < n_slots; ++s)
+	{
+		Slot& sl = ctx->slots[(size_t)s];
+		sl.dev = s % n_devices;
+		CREATE_CUDA(cudaSetDevice(ctx->devs[(size_t)sl.dev].id));
+		CREATE_CUDA(cudaHostAlloc(&sl.h_block, ctx->block_bytes, cudaHostAllocPortable));
+		CREATE_CUDA(cudaHostAlloc(&sl.h_res, (size_t)cap * sizeof(spg_result), cudaHostAllocPortable));
+		CREATE_CUDA(cudaMalloc(&sl.d_block, ctx->block_bytes));
+		CREATE_CUDA(cudaMalloc(&sl.d_res, (size_t)cap * sizeof(spg_result)));
+		CREATE_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+		memset(sl.h_block, 0, ctx->block_bytes);
+	}
+#undef CREATE_CUDA
+	*out = ctx;
+	return SPG_OK;
+}
+
+int spg_slot_buffers(spg_ctx* ctx, int slot, spg_slot_view* v)
+{
+	if (!ctx || !v) return SPG_ERR_PARAM;
+	if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, SPG_ERR_PARAM, "slot out of range");
+	Slot& sl = ctx->slots[(size_t)slot];
+	v->bases1 = sl.h_block;
+	v->quals1 = sl.h_block + ctx->plane_bytes;
+	v->bases2 = sl.h_block + 2 * ctx->plane_bytes;
+	v->quals2 = sl.h_block + 3 * ctx->plane_bytes;
+	v->len1 = reinterpret_cast<uint16_t*>(sl.h_block + 4 * ctx->plane_bytes);
+	v->len2 = reinterpret_cast<uint16_t*>(sl.h_block + 4 * ctx->plane_bytes + ctx->len_bytes);
+	v->stride = ctx->stride;
+	v->max_pairs = ctx->max_pairs;
+	return SPG_OK;
+}
+
+int spg_submit(spg_ctx* ctx, int slot, int n_pairs)
+{
+	if (!ctx) return SPG_ERR_PARAM;
+	if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, SPG_ERR_PARAM, "slot out of range");
+	if (n_pairs < 0 || n_pairs > ctx->max_pairs) return fail(ctx, SPG_ERR_PARAM, "n_pairs out of range");
+	Slot& sl = ctx->slots[(size_t)slot];
+	if (sl.state != SLOT_IDLE) return fail(ctx, SPG_ERR_STATE, "slot was submitted and not waited for");
+	Device& d = ctx->devs[(size_t)sl.dev];
+	SPG_CUDA(ctx, cudaSetDevice(d.id));
+	sl.n = n_pairs;
+	if (n_pairs > 0)
+	{
+		const size_t rows = (size_t)n_pairs * ctx->stride;
+		const size_t lens = (size_t)((n_pairs + 7) / 8 * 8) * sizeof(uint16_t);
+		const size_t pb = ctx->plane_bytes;
+		if (n_pairs == ctx->max_pairs)
+		{
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block, sl.h_block, ctx->block_bytes, cudaMemcpyHostToDevice, d.stream));
+		}
+		else
+		{
+			for (int k = 0; k < 4; ++k) SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + k * pb, sl.h_block + k * pb, rows, cudaMemcpyHostToDevice, d.stream));
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb, sl.h_block + 4 * pb, lens, cudaMemcpyHostToDevice, d.stream));
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb + ctx->len_bytes, sl.h_block + 4 * pb + ctx->len_bytes, lens, cudaMemcpyHostToDevice, d.stream));
+		}
+		int rc = launch_trim(ctx, d, sl.d_block, sl.d_block + pb, sl.d_block + 2 * pb, sl.d_block + 3 * pb, reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb),
+		                     reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.d_res, d.stream);
+		if (rc != SPG_OK) return rc;
+		SPG_CUDA(ctx, cudaMemcpyAsync(sl.h_res, sl.d_res, (size_t)n_pairs * sizeof(spg_result), cudaMemcpyDeviceToHost, d.stream));
+		if (ctx->params.ec) // edited rows come back in the slot
+		{
+			for (int k = 0; k < 4; ++k) SPG_CUDA(ctx, cudaMemcpyAsync(sl.h_block + k * pb, sl.d_block + k * pb, rows, cudaMemcpyDeviceToHost, d.stream));
+		}
+	}
+	SPG_CUDA(ctx, cudaEventRecord(sl.done, d.stream));
+	sl.state = SLOT_SUBMITTED;
+	return SPG_OK;
+}
+
+int spg_wait(spg_ctx* ctx, int slot, const spg_result** results)
+{
+	if (!ctx) return SPG_ERR_PARAM;
+	if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, SPG_ERR_PARAM, "slot out of range");
+	Slot& sl = ctx->slots[(size_t)slot];
+	if (sl.state != SLOT_SUBMITTED) return fail(ctx, SPG_ERR_STATE, "slot was not submitted");
+	SPG_CUDA(ctx, cudaEventSynchronize(sl.done));
+	sl.state = SLOT_IDLE;
+	if (results) *results = sl.h_res;
+	return SPG_OK;
+}
+
+int spg_trim_device(spg_ctx* ctx, int device_index, void* bases1, void* quals1, void* bases2, void* quals2, const uint16_t* len1, const uint16_t* len2, int stride,
+                    int64_t n_pairs, spg_result* results, void* cuda_stream)
+{
+	if (!ctx) return SPG_ERR_PARAM;
+	if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SPG_ERR_PARAM, "device index out of range");
+	if (stride < 16 || stride % 16 != 0 || stride > 1008) return fail(ctx, SPG_ERR_PARAM, "stride must be a multiple of 16 in [16,1008]");
+	const uintptr_t bits = (uintptr_t)bases1 | (uintptr_t)quals1 | (uintptr_t)bases2 | (uintptr_t)quals2 | (uintptr_t)len1 | (uintptr_t)len2;
+	if (bits & 15u) return fail(ctx, SPG_ERR_PARAM, "device pointers must be 16-byte aligned");
+	if ((uintptr_t)results & 7u) return fail(ctx, SPG_ERR_PARAM, "results must be 8-byte aligned");
+	if (n_pairs < 0) return fail(ctx, SPG_ERR_PARAM, "negative n_pairs");
+	Device& d = ctx->devs[(size_t)device_index];
+	SPG_CUDA(ctx, cudaSetDevice(d.id));
+	return launch_trim(ctx, d, (uint8_t*)bases1, (uint8_t*)quals1, (uint8_t*)bases2, (uint8_t*)quals2, len1, len2, stride, (long long)n_pairs, results,
+	                   (cudaStream_t)cuda_stream);
+}
+
+int spg_ec_stats_get(spg_ctx* ctx, spg_ec_stats* out)
+{
+	if (!ctx || !out) return SPG_ERR_PARAM;
+	memset(out, 0, sizeof(*out));
+	std::vector<unsigned long long> tmp(3 * SPG_MAXLEN);
+	for (Device& d : ctx->devs)
+	{
+		SPG_CUDA(ctx, cudaSetDevice(d.id));
+		SPG_CUDA(ctx, cudaMemcpy(tmp.data(), d.d_ec, tmp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+		for (int i = 0; i < SPG_MAXLEN; ++i)
+		{
+			out->mismatch_r1[i] += (int64_t)tmp[(size_t)i];
+			out->mismatch_r2[i] += (int64_t)tmp[(size_t)SPG_MAXLEN + i];
+			out->errors_per_read[i] += (int64_t)tmp[(size_t)2 * SPG_MAXLEN + i];
+		}
+	}
+	return SPG_OK;
+}
+
+const char* spg_last_error(spg_ctx* ctx)
+{
+	if (!ctx) return g_create_error.c_str();
+	std::lock_guard<std::mutex> g(ctx->mu);
+	return ctx->err.c_str();
+}
+
+void spg_destroy(spg_ctx* ctx)
+{
+	if (!ctx) return;
+	for (Slot& sl : ctx->slots)
+	{
+		if (sl.dev < (int)ctx->devs.size() && ctx->devs[(size_t)sl.dev].id >= 0) cudaSetDevice(ctx->devs[(size_t)sl.dev].id);
+		if (sl.done)
+		{
+			cudaEventSynchronize(sl.done);
+			cudaEventDestroy(sl.done);
+		}
+		if (sl.h_block) cudaFreeHost(sl.h_block);
+		if (sl.h_res) cudaFreeHost(sl.h_res);
+		if (sl.d_block) cudaFree(sl.d_block);
+		if (sl.d_res) cudaFree(sl.d_res);
+	}
+	for (Device& d : ctx->devs)
+	{
+		if (d.id < 0) continue;
+		cudaSetDevice(d.id);
+		if (d.stream)
+		{
+			cudaStreamSynchronize(d.stream);
+			cudaStreamDestroy(d.stream);
+		}
+		cudaFree(d.d_mmin);
+		cudaFree(d.d_rank);
+		cudaFree(d.d_psmall);
+		cudaFree(d.d_ec);
+	}
+	delete ctx;
+}
+
+int spg_set_option(spg_ctx* ctx, int option, int value)
+{
+	if (!ctx) return SPG_ERR_PARAM;
+	switch (option)
+	{
+		case SPG_OPT_FORCE_BYTEWISE: ctx->force_bytewise = value ? 1 : 0; return SPG_OK;
+		case SPG_OPT_GRID_CTAS_PER_SM: ctx->ctas_per_sm = value; return SPG_OK;
+		default: return fail(ctx, SPG_ERR_PARAM, "unknown option");
+	}
+}
+
+int64_t spg_launch_count(spg_ctx* ctx)
+{
+	if (!ctx) return 0;
+	std::lock_guard<std::mutex> g(ctx->mu);
+	return ctx->launches;
+}
+
+} // extern "C"

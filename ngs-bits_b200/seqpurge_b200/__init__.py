@@ -1,0 +1,249 @@
+"""seqpurge_b200 -- ctypes binding of libseqpurge_b200.so (the C ABI in include/seqpurge_b200.h).
+
+Host-side mirror, in Python, of the seam the library replaces in imgag/ngs-bits:
+``TrimmingParameters`` (src/SeqPurge/Auxilary.h:100-133) and the job hand-off of
+``ThreadCoordinator::analyze`` -> ``AnalysisWorker::run`` (src/SeqPurge/ThreadCoordinator.cpp:92-98,
+src/SeqPurge/AnalysisWorker.cpp:79-457).  torch is only plumbing here (device memory, streams, events);
+all trimming work happens in the CUDA library, and importing this module fails loudly if the library has
+not been built -- there is no Python or CPU fallback.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libseqpurge_b200.so")
+
+MAXLEN = 1000
+F_INSERT, F_ADAPTER, F_Q1, F_Q2, F_N1, F_N2 = 1, 2, 4, 8, 16, 32
+PAIR_OK, PAIR_BAD_BASE_R2, PAIR_TOO_LONG, PAIR_BAD_BASE_EC = 0, 1, 2, 3
+OPT_FORCE_BYTEWISE, OPT_GRID_CTAS_PER_SM = 1, 2
+
+RESULT_DTYPE = np.dtype([("len1", "<u2"), ("len2", "<u2"), ("best_offset", "<i2"), ("flags", "u1"), ("status", "u1")])
+assert RESULT_DTYPE.itemsize == 8
+
+DEFAULT_A1 = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"  # src/SeqPurge/main.cpp:25
+DEFAULT_A2 = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"  # src/SeqPurge/main.cpp:26
+
+
+class SeqPurgeError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a). seqpurge_b200 has no CPU fallback."
+    )
+_lib = C.CDLL(LIB_PATH)
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("a1", C.c_char_p), ("a1_len", C.c_int32), ("a2", C.c_char_p), ("a2_len", C.c_int32),
+        ("adapter_overlap", C.c_int32), ("match_perc", C.c_double), ("mep", C.c_double),
+        ("qcut", C.c_int32), ("qwin", C.c_int32), ("qoff", C.c_int32), ("ncut", C.c_int32), ("ec", C.c_int32),
+    ]
+
+
+class _SlotView(C.Structure):
+    _fields_ = [
+        ("bases1", C.c_void_p), ("quals1", C.c_void_p), ("bases2", C.c_void_p), ("quals2", C.c_void_p),
+        ("len1", C.c_void_p), ("len2", C.c_void_p), ("stride", C.c_int32), ("max_pairs", C.c_int32),
+    ]
+
+
+class _EcStats(C.Structure):
+    _fields_ = [("mismatch_r1", C.c_int64 * MAXLEN), ("mismatch_r2", C.c_int64 * MAXLEN), ("errors_per_read", C.c_int64 * MAXLEN)]
+
+
+class _SynthConfig(C.Structure):
+    _fields_ = [
+        ("read_len", C.c_int32), ("insert_mean", C.c_float), ("insert_sd", C.c_float), ("insert_min", C.c_int32),
+        ("insert_max", C.c_int32), ("error_rate", C.c_float), ("n_rate", C.c_float), ("lowq_tail_mean", C.c_float),
+        ("n_run_rate", C.c_float), ("binned_quals", C.c_int32), ("seed", C.c_uint64), ("a1", C.c_char_p), ("a2", C.c_char_p),
+    ]
+
+
+_lib.spg_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Params), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int]
+_lib.spg_create.restype = C.c_int
+_lib.spg_slot_buffers.argtypes = [C.c_void_p, C.c_int, C.POINTER(_SlotView)]
+_lib.spg_slot_buffers.restype = C.c_int
+_lib.spg_submit.argtypes = [C.c_void_p, C.c_int, C.c_int]
+_lib.spg_submit.restype = C.c_int
+_lib.spg_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+_lib.spg_wait.restype = C.c_int
+_lib.spg_trim_device.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
+_lib.spg_trim_device.restype = C.c_int
+_lib.spg_ec_stats_get.argtypes = [C.c_void_p, C.POINTER(_EcStats)]
+_lib.spg_ec_stats_get.restype = C.c_int
+_lib.spg_last_error.argtypes = [C.c_void_p]
+_lib.spg_last_error.restype = C.c_char_p
+_lib.spg_destroy.argtypes = [C.c_void_p]
+_lib.spg_destroy.restype = None
+_lib.spg_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+_lib.spg_set_option.restype = C.c_int
+_lib.spg_launch_count.argtypes = [C.c_void_p]
+_lib.spg_launch_count.restype = C.c_int64
+_lib.spg_synth_device.argtypes = [C.c_int, C.POINTER(_SynthConfig), C.c_int64, C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+_lib.spg_synth_device.restype = C.c_int
+
+
+@dataclass
+class TrimmingParameters:
+    """Fields of the reference's TrimmingParameters that the analysis step reads (Auxilary.h:100-133), with the
+    command-line defaults of src/SeqPurge/main.cpp:25-43."""
+
+    a1: str = DEFAULT_A1
+    a2: str = DEFAULT_A2
+    adapter_overlap: int = 10
+    match_perc: float = 80.0
+    mep: float = 0.000001
+    qcut: int = 15
+    qwin: int = 5
+    qoff: int = 33
+    ncut: int = 7
+    ec: bool = False
+
+    def _c(self):
+        a1, a2 = self.a1.encode(), self.a2.encode()
+        p = _Params(a1, len(a1), a2, len(a2), self.adapter_overlap, self.match_perc, self.mep, self.qcut, self.qwin, self.qoff, self.ncut, int(self.ec))
+        p._keep = (a1, a2)
+        return p
+
+
+@dataclass
+class SynthConfig:
+    """Synthetic read-pair stream."""
+
+    read_len: int = 150
+    insert_mean: float = 250.0
+    insert_sd: float = 80.0
+    insert_min: int = 1
+    insert_max: int = 2000
+    error_rate: float = 0.001
+    n_rate: float = 1e-4
+    lowq_tail_mean: float = 3.0
+    n_run_rate: float = 0.0
+    binned_quals: bool = False
+    seed: int = 0x5E9B200
+
+    def _c(self):
+        return _SynthConfig(self.read_len, self.insert_mean, self.insert_sd, self.insert_min, self.insert_max, self.error_rate, self.n_rate,
+                            self.lowq_tail_mean, self.n_run_rate, int(self.binned_quals), self.seed, None, None)
+
+
+def _np_view(ptr, shape, dtype):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    buf = (C.c_uint8 * n).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+class Slot:
+    """Pinned host SoA of one job (one AnalysisJob of the reference's pool)."""
+
+    def __init__(self, view):
+        self.stride, self.max_pairs = view.stride, view.max_pairs
+        shp = (view.max_pairs, view.stride)
+        self.bases1 = _np_view(view.bases1, shp, np.uint8)
+        self.quals1 = _np_view(view.quals1, shp, np.uint8)
+        self.bases2 = _np_view(view.bases2, shp, np.uint8)
+        self.quals2 = _np_view(view.quals2, shp, np.uint8)
+        self.len1 = _np_view(view.len1, (view.max_pairs,), np.uint16)
+        self.len2 = _np_view(view.len2, (view.max_pairs,), np.uint16)
+
+
+class Engine:
+    """One spg_ctx.  ``devices``: CUDA device ids; slot s runs on devices[s % len(devices)]."""
+
+    def __init__(self, params=None, devices=(0,), n_slots=0, max_pairs=0, max_len=0):
+        self.params = params or TrimmingParameters()
+        self._p = self.params._c()
+        self._h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices)
+        rc = _lib.spg_create(C.byref(self._h), C.byref(self._p), devs, len(devices), n_slots, max_pairs, max_len)
+        if rc != 0:
+            raise SeqPurgeError(f"spg_create failed ({rc}): {_lib.spg_last_error(None).decode()}")
+        self.n_slots, self.max_pairs, self.max_len = n_slots, max_pairs, max_len
+        self._slots = {}
+        self._pending = {}
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SeqPurgeError(f"{what} failed ({rc}): {_lib.spg_last_error(self._h).decode()}")
+
+    def slot(self, i):
+        if i not in self._slots:
+            v = _SlotView()
+            self._check(_lib.spg_slot_buffers(self._h, i, C.byref(v)), "spg_slot_buffers")
+            self._slots[i] = Slot(v)
+        return self._slots[i]
+
+    def submit(self, slot, n_pairs):
+        self._check(_lib.spg_submit(self._h, slot, n_pairs), "spg_submit")
+        self._pending[slot] = n_pairs
+
+    def wait(self, slot):
+        """Returns a structured array (RESULT_DTYPE) viewing the slot's pinned result records."""
+        res = C.c_void_p()
+        self._check(_lib.spg_wait(self._h, slot, C.byref(res)), "spg_wait")
+        n = self._pending.pop(slot)
+        if n == 0:
+            return np.zeros(0, RESULT_DTYPE)
+        return _np_view(res.value, (n,), RESULT_DTYPE)
+
+    def trim_device(self, bases1, quals1, bases2, quals2, len1, len2, results, n_pairs=None, device_index=0, stream=None):
+        """Device-resident batch (torch CUDA tensors): rows uint8 [n, stride], lens int16/uint16 [>= round_up(n, 8)],
+        results uint8 [n, 8] (or int64 [n]). Queued on `stream` (default: torch's current stream)."""
+        import torch
+
+        n = bases1.shape[0] if n_pairs is None else n_pairs
+        stride = bases1.stride(0)
+        if stream is None:
+            stream = torch.cuda.current_stream(bases1.device).cuda_stream
+        rc = _lib.spg_trim_device(self._h, device_index, bases1.data_ptr(), quals1.data_ptr(), bases2.data_ptr(), quals2.data_ptr(), len1.data_ptr(),
+                                  len2.data_ptr(), stride, n, results.data_ptr(), stream)
+        self._check(rc, "spg_trim_device")
+
+    def ec_stats(self):
+        st = _EcStats()
+        self._check(_lib.spg_ec_stats_get(self._h, C.byref(st)), "spg_ec_stats_get")
+        return {k: np.array(getattr(st, k), dtype=np.int64) for k in ("mismatch_r1", "mismatch_r2", "errors_per_read")}
+
+    def set_option(self, option, value):
+        self._check(_lib.spg_set_option(self._h, option, value), "spg_set_option")
+
+    @property
+    def launch_count(self):
+        return int(_lib.spg_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.spg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def synth_device(cfg, first_pair, n_pairs, bases1, quals1, bases2, quals2, len1, len2, device_id=0, stream=None):
+    """Fill torch CUDA tensors (rows uint8 [n, stride]) with pairs [first_pair, first_pair+n_pairs) of the stream `cfg`."""
+    import torch
+
+    if stream is None:
+        stream = torch.cuda.current_stream(bases1.device).cuda_stream
+    c = cfg._c()
+    rc = _lib.spg_synth_device(device_id, C.byref(c), first_pair, n_pairs, bases1.data_ptr(), quals1.data_ptr(), bases2.data_ptr(), quals2.data_ptr(),
+                               len1.data_ptr(), len2.data_ptr(), bases1.stride(0), stream)
+    if rc != 0:
+        raise SeqPurgeError(f"spg_synth_device failed ({rc})")
+
+
+def results_from_tensor(t):
+    """torch uint8 [n, 8] (CPU) -> structured array."""
+    return t.cpu().numpy().reshape(-1).view(RESULT_DTYPE)

@@ -1,0 +1,166 @@
+"""Test helpers: ctypes binding of the CPU oracle (oracle/), FASTQ fixtures -> SoA batches, synthetic batches in numpy."""
+import ctypes as C
+import gzip
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+RESULT_DTYPE = np.dtype([("len1", "<u2"), ("len2", "<u2"), ("best_offset", "<i2"), ("flags", "u1"), ("status", "u1")])
+MAXLEN = 1000
+DEFAULT_A1 = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCA"
+DEFAULT_A2 = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGT"
+
+
+class _SpoParams(C.Structure):
+    _fields_ = [
+        ("a1", C.c_char_p), ("a1_len", C.c_int), ("a2", C.c_char_p), ("a2_len", C.c_int), ("a_size", C.c_int),
+        ("adapter_overlap", C.c_int), ("match_perc", C.c_double), ("mep", C.c_double),
+        ("qcut", C.c_int), ("qwin", C.c_int), ("qoff", C.c_int), ("ncut", C.c_int), ("ec", C.c_int),
+    ]
+
+
+class _SpoEc(C.Structure):
+    _fields_ = [("mismatch_r1", C.c_int64 * MAXLEN), ("mismatch_r2", C.c_int64 * MAXLEN), ("errors_per_read", C.c_int64 * MAXLEN)]
+
+
+_oracle = None
+
+
+def build_oracle():
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True)
+    return os.path.join(ORACLE_DIR, "build")
+
+
+def oracle_lib():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(build_oracle(), "libseqpurge_oracle.so")
+        lib = C.CDLL(path)
+        lib.spo_trim_batch.argtypes = [C.POINTER(_SpoParams)] + [C.c_void_p] * 6 + [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
+        lib.spo_trim_batch.restype = None
+        lib.spo_match_probability.argtypes = [C.c_double, C.c_int, C.c_int]
+        lib.spo_match_probability.restype = C.c_double
+        lib.spo_factorial.argtypes = [C.c_int]
+        lib.spo_factorial.restype = C.c_double
+        lib.spo_trim_quality.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int]
+        lib.spo_trim_quality.restype = C.c_int
+        lib.spo_trim_n.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.c_int]
+        lib.spo_trim_n.restype = C.c_int
+        _oracle = lib
+    return _oracle
+
+
+def oracle_params(a1=DEFAULT_A1, a2=DEFAULT_A2, adapter_overlap=10, match_perc=80.0, mep=1e-6, qcut=15, qwin=5, qoff=33, ncut=7, ec=False):
+    b1, b2 = a1.encode(), a2.encode()
+    p = _SpoParams(b1, len(b1), b2, len(b2), min(20, len(b1), len(b2)), adapter_overlap, match_perc, mep, qcut, qwin, qoff, ncut, int(ec))
+    p._keep = (b1, b2)
+    return p
+
+
+class Batch:
+    """SoA batch in the slot layout of the C ABI: fixed-stride uint8 rows + uint16 lengths."""
+
+    def __init__(self, n, stride):
+        self.n, self.stride = n, stride
+        cap = (n + 7) // 8 * 8
+        self.bases1 = np.zeros((cap, stride), np.uint8)
+        self.quals1 = np.zeros((cap, stride), np.uint8)
+        self.bases2 = np.zeros((cap, stride), np.uint8)
+        self.quals2 = np.zeros((cap, stride), np.uint8)
+        self.len1 = np.zeros(cap, np.uint16)
+        self.len2 = np.zeros(cap, np.uint16)
+
+    def copy(self):
+        b = Batch(self.n, self.stride)
+        for k in ("bases1", "quals1", "bases2", "quals2", "len1", "len2"):
+            getattr(b, k)[...] = getattr(self, k)
+        return b
+
+    def set_pair(self, i, r1, q1, r2, q2):
+        assert len(r1) == len(q1) and len(r2) == len(q2)
+        self.bases1[i, : len(r1)] = np.frombuffer(r1, np.uint8)
+        self.quals1[i, : len(q1)] = np.frombuffer(q1, np.uint8)
+        self.bases2[i, : len(r2)] = np.frombuffer(r2, np.uint8)
+        self.quals2[i, : len(q2)] = np.frombuffer(q2, np.uint8)
+        self.len1[i], self.len2[i] = len(r1), len(r2)
+
+
+def oracle_trim(batch, threads=1, **params):
+    """Run the CPU oracle on a Batch. Returns (records, ec_stats or None); with ec=True the batch rows are edited in place."""
+    lib = oracle_lib()
+    p = oracle_params(**params)
+    out = np.zeros(batch.n, RESULT_DTYPE)
+    ec = _SpoEc() if params.get("ec") else None
+    lib.spo_trim_batch(C.byref(p), batch.bases1.ctypes.data, batch.quals1.ctypes.data, batch.bases2.ctypes.data, batch.quals2.ctypes.data,
+                       batch.len1.ctypes.data, batch.len2.ctypes.data, batch.stride, batch.n, out.ctypes.data, C.addressof(ec) if ec else None, threads)
+    ecd = None
+    if ec:
+        ecd = {k: np.array(getattr(ec, k), dtype=np.int64) for k in ("mismatch_r1", "mismatch_r2", "errors_per_read")}
+    return out, ecd
+
+
+def read_fastq(path):
+    """4-line FASTQ records (headers, bases, quals as bytes); tolerates a missing last quality line like the reference's reader."""
+    with gzip.open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    recs = []
+    for i in range(0, len(lines), 4):
+        chunk = [l.rstrip(b"\r") for l in lines[i : i + 4]] + [b""] * 4
+        recs.append((chunk[0], chunk[1], chunk[3]))
+    return recs
+
+
+def golden_batch(i1, i2, stride=None):
+    r1 = read_fastq(os.path.join(GOLDEN, f"SeqPurge_in{i1}.fastq.gz"))
+    r2 = read_fastq(os.path.join(GOLDEN, f"SeqPurge_in{i2}.fastq.gz"))
+    assert len(r1) == len(r2)
+    maxlen = max(max(len(r[1]) for r in r1), max(len(r[1]) for r in r2))
+    if stride is None:
+        stride = (maxlen + 15) // 16 * 16
+    b = Batch(len(r1), stride)
+    for i, (a, c) in enumerate(zip(r1, r2)):
+        b.set_pair(i, a[1], a[2], c[1], c[2])
+    return b
+
+
+def random_batch(n, L, seed, insert_mean=None, insert_sd=None, error_rate=0.01, n_rate=0.001, lowq_tail=5.0, a1=DEFAULT_A1, a2=DEFAULT_A2,
+                 ragged=False, n_runs=0.0, stride=None):
+    """Numpy restatement of the synthetic model (fragment + adapters + filler, errors, Ns, low-quality tails)."""
+    rng = np.random.default_rng(seed)
+    if stride is None:
+        stride = (L + 15) // 16 * 16
+    b = Batch(n, stride)
+    comp = {65: 84, 67: 71, 71: 67, 84: 65, 78: 78}
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    mu = insert_mean if insert_mean is not None else 1.2 * L
+    sd = insert_sd if insert_sd is not None else 0.5 * L
+    for i in range(n):
+        ins = int(np.clip(round(rng.normal(mu, sd)), 1, 4 * L))
+        frag = acgt[rng.integers(0, 4, ins)]
+        rc = np.array([comp[x] for x in frag[::-1]], np.uint8)
+        reads = []
+        for frag_o, ad in ((frag, a1), (rc, a2)):
+            ln = L if not ragged else int(rng.integers(0, L + 1))
+            ad_b = np.frombuffer(ad.encode(), np.uint8)
+            seq = np.concatenate([frag_o, ad_b, acgt[rng.integers(0, 4, L)]])[:ln].copy()
+            err = rng.random(ln) < error_rate
+            seq[err] = acgt[rng.integers(0, 4, int(err.sum()))]
+            seq[rng.random(ln) < n_rate] = 78
+            if n_runs > 0 and ln > 20 and rng.random() < n_runs:
+                s = int(rng.integers(0, ln - 12))
+                seq[s : s + int(rng.integers(7, 12))] = 78
+            q = np.full(ln, 73, np.uint8)
+            q[rng.random(ln) < 0.05] = 40
+            t = int(rng.exponential(lowq_tail)) if lowq_tail > 0 else 0
+            if t > 0:
+                q[max(0, ln - t):] = 35
+            reads.append((seq.tobytes(), q.tobytes()))
+        b.set_pair(i, reads[0][0], reads[0][1], reads[1][0], reads[1][1])
+    return b

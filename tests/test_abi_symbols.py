@@ -1,0 +1,57 @@
+"""CPU test: the C-ABI library builds for sm_100a, loads, and exports every function include/seqpurge_b200.h declares.
+No compute calls here (no GPU in this container)."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+
+    g.build()
+    return ctypes.CDLL(g.LIB)
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "seqpurge_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(spg_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_declares_the_seam():
+    names = declared_functions()
+    for required in ("spg_create", "spg_slot_buffers", "spg_submit", "spg_wait", "spg_trim_device", "spg_last_error", "spg_destroy"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} is declared in include/seqpurge_b200.h but not exported"
+
+
+def test_create_without_gpu_fails_loudly(lib):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    sys.path.insert(0, os.path.join(ROOT, "ngs-bits_b200"))
+    import seqpurge_b200 as sp
+
+    with pytest.raises(sp.SeqPurgeError, match="no CUDA device|CPU path"):
+        sp.Engine(sp.TrimmingParameters(), devices=(0,), n_slots=1, max_pairs=8, max_len=150)
+
+
+def test_struct_layouts_match_header():
+    sys.path.insert(0, os.path.join(ROOT, "ngs-bits_b200"))
+    import seqpurge_b200 as sp
+
+    assert sp.RESULT_DTYPE.itemsize == 8
+    assert ctypes.sizeof(sp._EcStats) == 3 * 1000 * 8
+    assert ctypes.sizeof(sp._SlotView) == 6 * 8 + 8

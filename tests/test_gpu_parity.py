@@ -1,0 +1,257 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA engine, called through the C ABI, against the CPU oracle on
+the same inputs -- bit-exact result records (integer/index work).
+
+Inputs: the reference's own SeqPurge fixtures (tests/golden, flags of src/tools-TEST/SeqPurge_Test.cpp:100-208), seeded random
+batches covering the edge cases of SURVEY.md appendix B (unequal and zero lengths, N runs, low-quality tails, overlaps > 170 bases,
+bytes outside ACGTN, reads of up to 999 bases), and device-generated synthetic batches of the BASELINE configs.
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import __graft_entry__ as g
+
+    g.build()
+    import seqpurge_b200
+
+    return seqpurge_b200
+
+
+def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, **params):
+    """Run a Batch through spg_submit/spg_wait (pinned slot, H2D, kernel, D2H). Returns records (+ edited batch, ec stats with ec)."""
+    p = sp.TrimmingParameters(**params)
+    chunk = chunk or batch.n
+    eng = sp.Engine(p, devices=(0,), n_slots=n_slots, max_pairs=chunk, max_len=min(batch.stride, 999))
+    if force_bytewise:
+        eng.set_option(sp.OPT_FORCE_BYTEWISE, 1)
+    out = np.zeros(batch.n, sp.RESULT_DTYPE)
+    edited = batch.copy() if params.get("ec") else None
+    starts = list(range(0, batch.n, chunk))
+    inflight = []
+    for k, st in enumerate(starts):
+        slot = k % n_slots
+        if len(inflight) == n_slots:  # retire in submission order
+            s0, st0, n0 = inflight.pop(0)
+            out[st0 : st0 + n0] = eng.wait(s0)
+            if edited is not None:
+                _copy_back(eng.slot(s0), edited, st0, n0)
+        n = min(chunk, batch.n - st)
+        s = eng.slot(slot)
+        assert s.stride == batch.stride
+        for name in ("bases1", "quals1", "bases2", "quals2"):
+            getattr(s, name)[:n] = getattr(batch, name)[st : st + n]
+        s.len1[:n] = batch.len1[st : st + n]
+        s.len2[:n] = batch.len2[st : st + n]
+        eng.submit(slot, n)
+        inflight.append((slot, st, n))
+    for s0, st0, n0 in inflight:
+        out[st0 : st0 + n0] = eng.wait(s0)
+        if edited is not None:
+            _copy_back(eng.slot(s0), edited, st0, n0)
+    ec = eng.ec_stats() if params.get("ec") else None
+    eng.close()
+    return out, edited, ec
+
+
+def _copy_back(slot, edited, st, n):
+    for name in ("bases1", "quals1", "bases2", "quals2"):
+        getattr(edited, name)[st : st + n] = getattr(slot, name)[:n]
+
+
+def assert_same(got, want, batch=None):
+    a, b = got.view(np.uint64), want.view(np.uint64)
+    if not np.array_equal(a, b):
+        bad = np.nonzero(a != b)[0]
+        i = int(bad[0])
+        msg = f"{len(bad)} of {len(a)} records differ; first at pair {i}: gpu={got[i]} oracle={want[i]}"
+        if batch is not None:
+            msg += f"\nR1={batch.bases1[i, : batch.len1[i]].tobytes()}\nR2={batch.bases2[i, : batch.len2[i]].tobytes()}"
+        raise AssertionError(msg)
+
+
+GOLDEN_CASES = [
+    ("test_01", 1, 2, dict(ncut=0, qcut=0)),
+    ("test_02", 3, 4, dict(ncut=0, qcut=0)),
+    ("test_03", 5, 6, dict(ncut=0, qcut=0)),
+    ("test_04", 7, 8, dict(a1="CTGTCTCTTATACACATCT", a2="CTGTCTCTTATACACATCT", ncut=0, qcut=0)),
+    ("test_05", 1, 2, dict(qcut=15, ncut=0)),
+    ("test_06", 1, 2, dict(ncut=7, qcut=0)),
+    ("test_07", 1, 2, dict(qcut=25)),
+    ("test_08", 9, 10, dict()),
+    ("test_09", 11, 12, dict()),
+]
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES, ids=[c[0] for c in GOLDEN_CASES])
+@pytest.mark.parametrize("bytewise", [False, True], ids=["planes", "bytewise"])
+def test_reference_fixtures(sp, case, bytewise):
+    """Inputs and flags of the reference's tool tests; the oracle reproduces the reference's golden outputs on them
+    (tests/test_oracle_golden.py), so equality with the oracle here is equality with the reference."""
+    _, i1, i2, params = case
+    batch = H.golden_batch(i1, i2)
+    want, _ = H.oracle_trim(batch, **params)
+    got, _, _ = gpu_trim(sp, batch, force_bytewise=bytewise, **params)
+    assert_same(got, want, batch)
+
+
+@pytest.mark.parametrize("bytewise", [False, True], ids=["planes", "bytewise"])
+def test_reference_fixture_error_correction(sp, bytewise):
+    """test_10 (-ec): edited bases/qualities, result records and the error histograms all match."""
+    params = dict(ncut=0, qcut=0, ec=True)
+    batch = H.golden_batch(1, 2)
+    ref = batch.copy()
+    want, want_ec = H.oracle_trim(ref, **params)
+    got, edited, got_ec = gpu_trim(sp, batch, force_bytewise=bytewise, **params)
+    assert_same(got, want, batch)
+    for name in ("bases1", "quals1", "bases2", "quals2"):
+        assert np.array_equal(getattr(edited, name)[: batch.n], getattr(ref, name)[: batch.n]), name
+    for k in want_ec:
+        assert np.array_equal(got_ec[k], want_ec[k]), k
+
+
+def test_multi_slot_in_order(sp):
+    """Several slots in flight, uneven last chunk: records come back in submission order (reference -threads 1 order)."""
+    batch = H.golden_batch(5, 6)
+    want, _ = H.oracle_trim(batch)
+    got, _, _ = gpu_trim(sp, batch, n_slots=3, chunk=1000)
+    assert_same(got, want, batch)
+
+
+@pytest.mark.parametrize("L,seed", [(150, 1), (151, 2), (100, 3), (36, 4), (250, 5), (300, 6)])
+def test_random_batches(sp, L, seed):
+    batch = H.random_batch(3000, L, seed, error_rate=0.02, n_rate=0.002, lowq_tail=8.0)
+    want, _ = H.oracle_trim(batch)
+    got, _, _ = gpu_trim(sp, batch)
+    assert_same(got, want, batch)
+    assert (want["flags"] & 1).sum() > 100 and (want["flags"] & 2).sum() > 10  # both trimming modes exercised
+
+
+def test_random_ragged_lengths_and_n_runs(sp):
+    """len1 != len2, zero-length reads, injected N runs, -ncut/-qcut on (appendix B)."""
+    batch = H.random_batch(4000, 150, 11, ragged=True, n_runs=0.2, n_rate=0.01, lowq_tail=20.0)
+    want, _ = H.oracle_trim(batch, qcut=20, ncut=7)
+    got, _, _ = gpu_trim(sp, batch, qcut=20, ncut=7)
+    assert_same(got, want, batch)
+    assert (want["flags"] & 0x30).any() and (want["flags"] & 0x0C).any()
+    got2, _, _ = gpu_trim(sp, batch, force_bytewise=True, qcut=20, ncut=7)
+    assert_same(got2, want, batch)
+
+
+def test_high_overlap_halving_path(sp):
+    """2x250 with inserts below the read length: overlaps of more than 170 compared bases take matchProbability's halving path."""
+    batch = H.random_batch(2000, 250, 21, insert_mean=150, insert_sd=40, error_rate=0.02)
+    want, _ = H.oracle_trim(batch)
+    got, _, _ = gpu_trim(sp, batch)
+    assert_same(got, want, batch)
+    assert ((want["flags"] & 1) != 0).mean() > 0.9
+
+
+def test_long_reads_up_to_maxlen(sp):
+    """Reads of 400..999 bases run through the byte-wise path (MAXLEN-1 is the longest the reference accepts)."""
+    batch = H.random_batch(300, 999, 31, insert_mean=700, insert_sd=300, ragged=True)
+    want, _ = H.oracle_trim(batch)
+    got, _, _ = gpu_trim(sp, batch)
+    assert_same(got, want, batch)
+
+
+def test_bytes_outside_acgtn(sp):
+    """Read 1 may hold any byte (compared as a plain byte, AnalysisWorker.cpp:155-168); read 2 must be ACGTN or the reference throws
+    (Sequence.cpp:46-71) -> status 1."""
+    batch = H.random_batch(600, 150, 41, error_rate=0.01)
+    rng = np.random.default_rng(5)
+    for i in range(0, 600, 3):
+        j = int(rng.integers(0, batch.len1[i]))
+        batch.bases1[i, j] = rng.choice(np.frombuffer(b"acgtnXR.-", np.uint8))
+    for i in range(1, 600, 50):
+        j = int(rng.integers(0, batch.len2[i]))
+        batch.bases2[i, j] = ord("a")
+    batch.quals1[7, :20] = 200  # quality bytes >= 0x80 are negative chars in the reference (FastqFileStream.h:23-26)
+    want, _ = H.oracle_trim(batch)
+    assert (want["status"] == 1).sum() == 12
+    got, _, _ = gpu_trim(sp, batch)
+    assert_same(got, want, batch)
+
+
+def test_custom_parameters(sp):
+    """Non-default -match_perc / -mep / -qwin / -qoff / adapters with N."""
+    batch = H.random_batch(2500, 120, 51, error_rate=0.05, lowq_tail=15.0, a1="AGATCGGAAGAGCNCACGTCTGAACTCC", a2="AGATCGGAAGAGCGTCGTNTAGGGAAAG")
+    params = dict(a1="AGATCGGAAGAGCNCACGTCTGAACTCC", a2="AGATCGGAAGAGCGTCGTNTAGGGAAAG", match_perc=70.0, mep=1e-4, qcut=22, qwin=9, qoff=30, ncut=3)
+    want, _ = H.oracle_trim(batch, **params)
+    got, _, _ = gpu_trim(sp, batch, **params)
+    assert_same(got, want, batch)
+
+
+def test_empty_and_tiny_batches(sp):
+    eng = sp.Engine(sp.TrimmingParameters(), devices=(0,), n_slots=1, max_pairs=16, max_len=150)
+    eng.submit(0, 0)
+    assert len(eng.wait(0)) == 0
+    eng.close()
+    batch = H.random_batch(1, 150, 61)
+    want, _ = H.oracle_trim(batch)
+    got, _, _ = gpu_trim(sp, batch)
+    assert_same(got, want, batch)
+
+
+def test_slot_protocol_errors(sp):
+    eng = sp.Engine(sp.TrimmingParameters(), devices=(0,), n_slots=1, max_pairs=16, max_len=150)
+    with pytest.raises(sp.SeqPurgeError, match="not submitted"):
+        eng.wait(0)
+    eng.submit(0, 4)
+    with pytest.raises(sp.SeqPurgeError, match="not waited"):
+        eng.submit(0, 4)
+    eng.wait(0)
+    with pytest.raises(sp.SeqPurgeError):
+        eng.submit(0, 17)
+    eng.close()
+    with pytest.raises(sp.SeqPurgeError, match="15"):
+        sp.Engine(sp.TrimmingParameters(a1="ACGT"), devices=(0,), n_slots=1, max_pairs=16, max_len=150)
+
+
+SYNTH = {
+    "C2_2x150": (dict(read_len=150, insert_mean=250, insert_sd=80, error_rate=0.001, lowq_tail_mean=3.0), dict()),
+    "C3_2x250_high_overlap": (dict(read_len=250, insert_mean=150, insert_sd=40, insert_max=249, error_rate=0.001, lowq_tail_mean=3.0), dict()),
+    "C4_2x150_errors_lowq": (dict(read_len=150, insert_mean=250, insert_sd=80, error_rate=0.02, lowq_tail_mean=20.0, n_run_rate=0.005), dict(qcut=15, ncut=7)),
+    "C5_novaseq_like": (dict(read_len=150, insert_mean=350, insert_sd=100, error_rate=0.002, lowq_tail_mean=2.0, binned_quals=True), dict()),
+}
+
+
+@pytest.mark.parametrize("name", list(SYNTH), ids=list(SYNTH))
+def test_device_synthetic_configs(sp, name):
+    """BASELINE configs 2-5: batches generated on the device (first slice and a far slice of the stream), trimmed device-resident
+    (spg_trim_device on torch tensors), copied back and compared with the oracle on the same bytes."""
+    import torch
+
+    cfg_kw, params = SYNTH[name]
+    cfg = sp.SynthConfig(**cfg_kw)
+    n = 20000
+    stride = (cfg.read_len + 15) // 16 * 16
+    dev = torch.device("cuda:0")
+    eng = sp.Engine(sp.TrimmingParameters(**params), devices=(0,))
+    for first in (0, 99_000_000):
+        t = {k: torch.empty((n, stride), dtype=torch.uint8, device=dev) for k in ("bases1", "quals1", "bases2", "quals2")}
+        l1 = torch.empty(n, dtype=torch.int16, device=dev)
+        l2 = torch.empty(n, dtype=torch.int16, device=dev)
+        res = torch.empty((n, 8), dtype=torch.uint8, device=dev)
+        sp.synth_device(cfg, first, n, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
+        eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, res)
+        torch.cuda.synchronize()
+        got = sp.results_from_tensor(res)
+        batch = H.Batch(n, stride)
+        for k in t:
+            getattr(batch, k)[:n] = t[k].cpu().numpy()
+        batch.len1[:n] = l1.cpu().numpy().view(np.uint16)
+        batch.len2[:n] = l2.cpu().numpy().view(np.uint16)
+        want, _ = H.oracle_trim(batch, threads=8, **params)
+        assert_same(got, want, batch)
+        assert (want["status"] == 0).all()
+    eng.close()
