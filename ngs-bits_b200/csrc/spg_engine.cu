@@ -128,6 +128,25 @@ bool build_tables(const spg_params& p, int a_size, HostTables& t, std::string& e
 			t.ranktab[(size_t)count * spg::kRankDim + n] = (uint16_t)(std::lower_bound(ps.begin(), ps.end(), v) - ps.begin());
 		}
 	}
+	// Fold the -mep test into the pre-filter where no halving is involved (T <= 170): an offset with T compared bases needs
+	// at least mmin[T] matches to pass -match_perc AND to have p <= mep. Only done when the pass set is an upper interval in
+	// m (it always is for a binomial tail; verified here rather than assumed), so the filter stays exact.
+	for (int T = 1; T < spg::kRankDim; ++T)
+	{
+		int first = T + 1;
+		for (int m = 0; m <= T; ++m)
+			if (t.ranktab[(size_t)T * spg::kRankDim + m] != 0xFFFF)
+			{
+				first = m;
+				break;
+			}
+		bool interval = true;
+		for (int m = first; m <= T; ++m)
+			if (t.ranktab[(size_t)T * spg::kRankDim + m] == 0xFFFF) interval = false;
+		if (!interval) continue;
+		if (first > T) t.mmin[T] = 0xFFFF;
+		else if (t.mmin[T] != 0xFFFF && first > t.mmin[T]) t.mmin[T] = (uint16_t)first;
+	}
 	// probabilities of the short adapter fragments of the presence check
 	const int ao = p.adapter_overlap;
 	t.psmall.assign((size_t)(ao + 1) * (ao + 1), 1.0);
@@ -186,7 +205,7 @@ struct Device
 	uint16_t* d_rank = nullptr;
 	double* d_psmall = nullptr;
 	unsigned long long* d_ec = nullptr; // 3 * SPG_MAXLEN
-	int occ[4] = {0, 0, 0, 0};          // resident CTAs per SM for NW = 0,5,8,10 at the configured smem size
+	int occ[4][3] = {};                 // resident CTAs per SM for NW = 0,5,8,10 x consumer warps 4,6,8
 };
 
 enum SlotState
@@ -224,6 +243,9 @@ struct spg_ctx
 	std::mutex mu;
 	int force_bytewise = 0;
 	int ctas_per_sm = 0; // 0 = occupancy
+	int consumer_warps = 8;
+	int tile_pairs = 0; // 0 = automatic
+	int stages = 0;     // 0 = automatic
 	long long launches = 0;
 	spg_ec_stats ec_total;
 };
@@ -261,29 +283,34 @@ void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 	smem = (size_t)stages * (4 * (size_t)tp * stride + 4 * (size_t)tp);
 }
 
-template <int NW>
-cudaError_t launch_nw(const spg::KArgs& a, int grid, size_t smem, cudaStream_t stream)
+template <int NW, int CW>
+cudaError_t launch_cfg(const spg::KArgs& a, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, int* occ_cache)
 {
-	static thread_local size_t configured[64] = {0};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (dev < 64 && configured[dev] < smem)
+	// per (device, instantiation): raise the dynamic shared memory limit once, ask the occupancy calculator once
+	if (*occ_cache == 0)
 	{
-		cudaError_t e = cudaFuncSetAttribute(spg::trim_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaFuncSetAttribute(spg::trim_kernel<NW, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return e;
-		configured[dev] = smem;
+		int n = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::trim_kernel<NW, CW>, (CW + 1) * 32, smem);
+		if (e != cudaSuccess) return e;
+		*occ_cache = n < 1 ? 1 : n;
 	}
-	spg::trim_kernel<NW><<<grid, spg::kThreads, smem, stream>>>(a);
+	const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, *occ_cache) : *occ_cache;
+	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * per_sm);
+	spg::trim_kernel<NW, CW><<<grid, (CW + 1) * 32, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 
 template <int NW>
-int occupancy_nw(size_t smem)
+cudaError_t launch_nw(const spg::KArgs& a, int cw, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, int* occ_cache)
 {
-	cudaFuncSetAttribute(spg::trim_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	int n = 0;
-	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::trim_kernel<NW>, spg::kThreads, smem) != cudaSuccess) n = 1;
-	return n < 1 ? 1 : n;
+	switch (cw)
+	{
+		case 4: return launch_cfg<NW, 4>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
+		case 6: return launch_cfg<NW, 6>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
+		default: return launch_cfg<NW, 8>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
+	}
 }
 
 int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride, long long n,
@@ -303,6 +330,10 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	a.stride = stride;
 	size_t smem;
 	tile_geometry(stride, a.tile_pairs, a.stages, smem);
+	if (ctx->tile_pairs > 0) a.tile_pairs = ctx->tile_pairs;
+	if (ctx->stages > 0) a.stages = ctx->stages;
+	smem = (size_t)a.stages * (4 * (size_t)a.tile_pairs * stride + 4 * (size_t)a.tile_pairs);
+	if (smem > 200 * 1024) return fail(ctx, SPG_ERR_PARAM, "tile geometry exceeds shared memory");
 	a.mmin = d.d_mmin;
 	a.ranktab = d.d_rank;
 	a.psmall = d.d_psmall;
@@ -329,27 +360,16 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	memcpy(a.a2, ctx->a2.data(), std::min<size_t>(32, ctx->a2.size()));
 
 	const int nw = nw_for_stride(stride);
-	int& occ = d.occ[nw_index(nw)];
-	if (occ == 0)
-	{
-		switch (nw)
-		{
-			case 5: occ = occupancy_nw<5>(smem); break;
-			case 8: occ = occupancy_nw<8>(smem); break;
-			case 10: occ = occupancy_nw<10>(smem); break;
-			default: occ = occupancy_nw<0>(smem); break;
-		}
-	}
+	const int cw = ctx->consumer_warps;
+	int* occ = &d.occ[nw_index(nw)][cw == 4 ? 0 : cw == 6 ? 1 : 2];
 	const long long n_tiles = (n + a.tile_pairs - 1) / a.tile_pairs;
-	const int per_sm = ctx->ctas_per_sm > 0 ? std::min(ctx->ctas_per_sm, occ) : occ;
-	const int grid = (int)std::min<long long>(n_tiles, (long long)d.sm_count * per_sm);
 	cudaError_t e;
 	switch (nw)
 	{
-		case 5: e = launch_nw<5>(a, grid, smem, stream); break;
-		case 8: e = launch_nw<8>(a, grid, smem, stream); break;
-		case 10: e = launch_nw<10>(a, grid, smem, stream); break;
-		default: e = launch_nw<0>(a, grid, smem, stream); break;
+		case 5: e = launch_nw<5>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
+		case 8: e = launch_nw<8>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
+		case 10: e = launch_nw<10>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
+		default: e = launch_nw<0>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
 	}
 	if (e != cudaSuccess) return fail(ctx, SPG_ERR_CUDA, std::string("trim_kernel launch: ") + cudaGetErrorString(e));
 	{
@@ -613,6 +633,20 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 	{
 		case SPG_OPT_FORCE_BYTEWISE: ctx->force_bytewise = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_GRID_CTAS_PER_SM: ctx->ctas_per_sm = value; return SPG_OK;
+		case SPG_OPT_CONSUMER_WARPS:
+			if (value != 4 && value != 6 && value != 8) return fail(ctx, SPG_ERR_PARAM, "consumer warps must be 4, 6 or 8");
+			ctx->consumer_warps = value;
+			return SPG_OK;
+		case SPG_OPT_TILE_PAIRS:
+			if (value < 0 || value % 8 != 0 || value > 256) return fail(ctx, SPG_ERR_PARAM, "tile pairs must be a multiple of 8, at most 256");
+			ctx->tile_pairs = value;
+			for (Device& d : ctx->devs) memset(d.occ, 0, sizeof(d.occ));
+			return SPG_OK;
+		case SPG_OPT_STAGES:
+			if (value < 0 || value > spg::kMaxStages || value == 1) return fail(ctx, SPG_ERR_PARAM, "stages must be 2..4");
+			ctx->stages = value;
+			for (Device& d : ctx->devs) memset(d.occ, 0, sizeof(d.occ));
+			return SPG_OK;
 		default: return fail(ctx, SPG_ERR_PARAM, "unknown option");
 	}
 }
