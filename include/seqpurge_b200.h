@@ -135,7 +135,7 @@ void spg_destroy(spg_ctx* ctx);
 
 #define SPG_OPT_FORCE_BYTEWISE 1 /* value 1: route every pair through the byte-wise kernel path (cross-check of the bit-plane path) */
 #define SPG_OPT_GRID_CTAS_PER_SM 2 /* cap on resident CTAs per SM (0 = what the occupancy calculator allows) */
-#define SPG_OPT_CONSUMER_WARPS 3  /* consumer warps per CTA: 4, 6 or 8 (+1 producer warp) */
+#define SPG_OPT_MIN_BLOCKS 3      /* kernel variant compiled for at least 2, 3 or 4 resident CTAs per SM (register budget) */
 #define SPG_OPT_TILE_PAIRS 4      /* pairs per TMA-staged tile (multiple of 8; 0 = automatic) */
 #define SPG_OPT_STAGES 5          /* depth of the TMA ring, 2..4 (0 = automatic) */
 int spg_set_option(spg_ctx* ctx, int option, int value);

@@ -205,7 +205,7 @@ struct Device
 	uint16_t* d_rank = nullptr;
 	double* d_psmall = nullptr;
 	unsigned long long* d_ec = nullptr; // 3 * SPG_MAXLEN
-	int occ[4][3] = {};                 // resident CTAs per SM for NW = 0,5,8,10 x consumer warps 4,6,8
+	int occ[4][3] = {};                 // resident CTAs per SM for NW = 0,5,8,10 x kernel variant (min blocks 2,3,4)
 };
 
 enum SlotState
@@ -243,7 +243,7 @@ struct spg_ctx
 	std::mutex mu;
 	int force_bytewise = 0;
 	int ctas_per_sm = 0; // 0 = occupancy
-	int consumer_warps = 8;
+	int min_blocks = 3; // __launch_bounds__ min CTAs/SM of the kernel variant (register budget)
 	int tile_pairs = 0; // 0 = automatic
 	int stages = 0;     // 0 = automatic
 	long long launches = 0;
@@ -283,33 +283,35 @@ void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 	smem = (size_t)stages * (4 * (size_t)tp * stride + 4 * (size_t)tp);
 }
 
-template <int NW, int CW>
+constexpr int kCW = 8; // consumer warps per CTA (+1 producer warp); geometry sweeps showed 4/6/8 within 3%
+
+template <int NW, int MINB>
 cudaError_t launch_cfg(const spg::KArgs& a, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, int* occ_cache)
 {
 	// per (device, instantiation): raise the dynamic shared memory limit once, ask the occupancy calculator once
 	if (*occ_cache == 0)
 	{
-		cudaError_t e = cudaFuncSetAttribute(spg::trim_kernel<NW, CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaFuncSetAttribute(spg::trim_kernel<NW, kCW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return e;
 		int n = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::trim_kernel<NW, CW>, (CW + 1) * 32, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::trim_kernel<NW, kCW, MINB>, (kCW + 1) * 32, smem);
 		if (e != cudaSuccess) return e;
 		*occ_cache = n < 1 ? 1 : n;
 	}
 	const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, *occ_cache) : *occ_cache;
 	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * per_sm);
-	spg::trim_kernel<NW, CW><<<grid, (CW + 1) * 32, smem, stream>>>(a);
+	spg::trim_kernel<NW, kCW, MINB><<<grid, (kCW + 1) * 32, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 
 template <int NW>
-cudaError_t launch_nw(const spg::KArgs& a, int cw, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, int* occ_cache)
+cudaError_t launch_nw(const spg::KArgs& a, int minb, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, int* occ_cache)
 {
-	switch (cw)
+	switch (minb)
 	{
+		case 2: return launch_cfg<NW, 2>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
 		case 4: return launch_cfg<NW, 4>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
-		case 6: return launch_cfg<NW, 6>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
-		default: return launch_cfg<NW, 8>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
+		default: return launch_cfg<NW, 3>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
 	}
 }
 
@@ -360,8 +362,8 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	memcpy(a.a2, ctx->a2.data(), std::min<size_t>(32, ctx->a2.size()));
 
 	const int nw = nw_for_stride(stride);
-	const int cw = ctx->consumer_warps;
-	int* occ = &d.occ[nw_index(nw)][cw == 4 ? 0 : cw == 6 ? 1 : 2];
+	const int cw = ctx->min_blocks;
+	int* occ = &d.occ[nw_index(nw)][cw == 2 ? 0 : cw == 4 ? 2 : 1];
 	const long long n_tiles = (n + a.tile_pairs - 1) / a.tile_pairs;
 	cudaError_t e;
 	switch (nw)
@@ -633,9 +635,9 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 	{
 		case SPG_OPT_FORCE_BYTEWISE: ctx->force_bytewise = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_GRID_CTAS_PER_SM: ctx->ctas_per_sm = value; return SPG_OK;
-		case SPG_OPT_CONSUMER_WARPS:
-			if (value != 4 && value != 6 && value != 8) return fail(ctx, SPG_ERR_PARAM, "consumer warps must be 4, 6 or 8");
-			ctx->consumer_warps = value;
+		case SPG_OPT_MIN_BLOCKS:
+			if (value != 2 && value != 3 && value != 4) return fail(ctx, SPG_ERR_PARAM, "min blocks must be 2, 3 or 4");
+			ctx->min_blocks = value;
 			return SPG_OK;
 		case SPG_OPT_TILE_PAIRS:
 			if (value < 0 || value % 8 != 0 || value > 256) return fail(ctx, SPG_ERR_PARAM, "tile pairs must be a multiple of 8, at most 256");

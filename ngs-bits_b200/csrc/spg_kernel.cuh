@@ -246,17 +246,20 @@ __device__ __forceinline__ int trim_quality_warp(const KArgs& A, uint32_t q, int
 	const int window = A.qwin;
 	if (count < window) return count;
 	int count_new;
-	if (window <= 16)
+	if (window <= 32)
 	{
-		// blocks of 32 positions from the 3' end; lane l holds q[base+l] and sums its window with shuffles, so the
-		// window starts base .. base+32-window are decided per block (one load per lane)
+		// blocks of 32 positions from the 3' end: lane l holds q[base+l]; an inclusive warp scan gives every window sum as a
+		// difference of two prefix sums, so the window starts base .. base+32-window are decided per block with one load per lane
 		count_new = -1;
 		for (int base = count - 32; base + 32 - window >= 0; base -= 33 - window)
 		{
 			const int i = base + lane;
 			const int v = i >= 0 ? qual_at(q, i, A.qoff) : 0;
-			int s = v;
-			for (int w = 1; w < window; ++w) s += __shfl_down_sync(kFull, v, w);
+			int p = v;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) // p += (lane >= d) ? shfl_up(p, d) : 0
+				asm volatile("{\n\t.reg .pred g;\n\t.reg .s32 t;\n\tshfl.sync.up.b32 t|g, %0, %1, 0, 0xffffffff;\n\t@g add.s32 %0, %0, t;\n\t}" : "+r"(p) : "r"(d));
+			const int s = __shfl_sync(kFull, p, lane + window - 1) - p + v; // q[i] + ... + q[i+window-1] for lane <= 32-window
 			const bool ok = i >= 0 && lane <= 32 - window && s >= A.qthr;
 			const uint32_t b = __ballot_sync(kFull, ok);
 			if (b)
@@ -611,9 +614,10 @@ __device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTab
 	const uint32_t amask = ((1u << A.a_size) - 1u) & ~an;
 	const int tot_full = __popc(amask);
 	const uint32_t pass_full = T.passA[tot_full];
-	int found = -1;
+	uint32_t hit[NW];
+	uint32_t any = 0;
 #pragma unroll
-	for (int q = NW - 1; q >= 0; --q) // descending, so that the lowest hit is kept
+	for (int q = 0; q < NW; ++q)
 	{
 		bool pass;
 		if (!HASN && 32 * q + 31 + A.a_size <= len) // warp-uniform: every lane has the full adapter window inside the read
@@ -630,9 +634,14 @@ __device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTab
 			const int tot = __popc(valid);
 			pass = cnt > 0 && ((T.passA[tot] >> (tot - __popc(x))) & 1u);
 		}
-		const uint32_t b = __ballot_sync(kFull, pass);
-		if (b) found = 32 * q + __ffs(b) - 1;
+		hit[q] = __ballot_sync(kFull, pass);
+		any |= hit[q];
 	}
+	if (any == 0) return -1; // the common case
+	int found = -1;
+#pragma unroll
+	for (int q = NW - 1; q >= 0; --q)
+		if (hit[q]) found = 32 * q + __ffs(hit[q]) - 1;
 	return found;
 }
 
@@ -810,8 +819,8 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 // dynamic shared memory: [stages][ b1 | q1 | b2 | q2 : tile_pairs*stride each ][ len1 | len2 : tile_pairs u16 each ]
 // Within a tile the consumer warps claim pairs one at a time from a shared counter, so that a warp that drew cheap pairs
 // (insert hit: no adapter scans) takes more of them and all warps release the stage at about the same time.
-template <int NW, int CW>
-__global__ void __launch_bounds__((CW + 1) * 32) trim_kernel(const __grid_constant__ KArgs A)
+template <int NW, int CW, int MINB>
+__global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_constant__ KArgs A)
 {
 	constexpr int kThreads = (CW + 1) * 32;
 	extern __shared__ __align__(128) uint8_t smem[];

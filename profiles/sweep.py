@@ -32,13 +32,13 @@ for b in range(2):
     bufs.append((t, l1, l2))
 res = torch.empty((n, 8), dtype=torch.uint8, device=dev)
 eng = sp.Engine(sp.TrimmingParameters(), devices=(0,))
-grid = list(itertools.product((4, 6, 8), (16, 32, 64), (2, 3, 4), (0,)))
+grid = list(itertools.product((2, 3, 4), (16, 32), (2, 3), (0,)))
 if len(sys.argv) > 3:
     grid = [tuple(int(x) for x in c.split(",")) for c in sys.argv[3:]]
 ref = None
 for cw, tp, ns, cap in grid:
     try:
-        eng.set_option(sp.OPT_CONSUMER_WARPS, cw)
+        eng.set_option(sp.OPT_MIN_BLOCKS, cw)
         eng.set_option(sp.OPT_TILE_PAIRS, tp)
         eng.set_option(sp.OPT_STAGES, ns)
         eng.set_option(sp.OPT_GRID_CTAS_PER_SM, cap)
@@ -60,6 +60,6 @@ for cw, tp, ns, cap in grid:
         chk = int(res.view(torch.int64).sum().item())
         if ref is None:
             ref = chk
-        print(f"cw={cw} tile={tp} stages={ns} cap={cap}: {ms:.3f} ms  {n / ms / 1e3:.1f} Mpairs/s  {'ok' if chk == ref else 'RESULT MISMATCH'}", flush=True)
+        print(f"minb={cw} tile={tp} stages={ns} cap={cap}: {ms:.3f} ms  {n / ms / 1e3:.1f} Mpairs/s  {'ok' if chk == ref else 'RESULT MISMATCH'}", flush=True)
     except Exception as ex:  # noqa: BLE001
-        print(f"cw={cw} tile={tp} stages={ns} cap={cap}: failed: {ex}", flush=True)
+        print(f"minb={cw} tile={tp} stages={ns} cap={cap}: failed: {ex}", flush=True)

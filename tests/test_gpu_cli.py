@@ -1,0 +1,86 @@
+"""GPU tests of the drop-in command line (ngs-bits_b200/bin/seqpurge_b200 = reference flags + reference I/O surface + CUDA engine):
+the reference's ten single-thread tool tests (src/tools-TEST/SeqPurge_Test.cpp:100-208) re-run against the reference's own golden
+outputs, compared like the reference's COMPARE_FILES does (decompressed content), plus gz byte identity with the oracle CLI, which
+issues the same zlib call sequence as the reference (src/cppNGS/FastqFileStream.cpp:160-193)."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+import helpers as H
+from test_oracle_golden import CASES, COMMON
+
+pytestmark = pytest.mark.gpu
+G = H.GOLDEN
+ROOT = H.ROOT
+CLI = os.path.join(ROOT, "ngs-bits_b200", "bin", "seqpurge_b200")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import __graft_entry__ as g
+
+    g.build()
+    assert os.path.exists(CLI)
+    return CLI
+
+
+def _content(path):
+    with gzip.open(path, "rb") as f:
+        return f.read()
+
+
+def _raw(path):
+    with open(path, "rb") as f:
+        return f.read()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_cli_reproduces_reference_goldens(cli, case, oracle_build, tmp_path):
+    name, i1, i2, o1, o2, flags = case
+    outs = {}
+    for tool, exe in (("gpu", cli), ("oracle", os.path.join(oracle_build, "seqpurge_oracle"))):
+        d = tmp_path / tool
+        d.mkdir()
+        fl = [str(d / "out15") if f == "OUT3" else f for f in flags]
+        cmd = [exe, "-in1", f"{G}/SeqPurge_in{i1}.fastq.gz", "-in2", f"{G}/SeqPurge_in{i2}.fastq.gz", "-out1", str(d / "o1.fastq.gz"), "-out2", str(d / "o2.fastq.gz"),
+               "-summary", str(d / "summary.txt")] + COMMON + fl
+        subprocess.run(cmd, check=True)
+        outs[tool] = d
+    g = outs["gpu"]
+    # the reference's golden files, decompressed content (what COMPARE_FILES checks)
+    assert _content(g / "o1.fastq.gz") == _content(f"{G}/SeqPurge_out{o1}.fastq.gz")
+    assert _content(g / "o2.fastq.gz") == _content(f"{G}/SeqPurge_out{o2}.fastq.gz")
+    if name == "test_07":
+        assert _content(g / "out15_R1.fastq.gz") == _content(f"{G}/SeqPurge_out15_R1.fastq.gz")
+        assert _content(g / "out15_R2.fastq.gz") == _content(f"{G}/SeqPurge_out15_R2.fastq.gz")
+    # gz bytes: identical to the oracle CLI
+    assert _raw(g / "o1.fastq.gz") == _raw(outs["oracle"] / "o1.fastq.gz")
+    assert _raw(g / "o2.fastq.gz") == _raw(outs["oracle"] / "o2.fastq.gz")
+    # statistics summary (everything except the runtime line)
+    def summ(p):
+        return [l for l in open(p).read().split("\n") if not l.startswith("overall runtime")]
+    assert summ(g / "summary.txt") == summ(outs["oracle"] / "summary.txt")
+
+
+def test_cli_multiple_input_files_and_small_prefetch(cli, tmp_path):
+    """A block may span an input-file boundary (InputWorker.cpp:26-38); few slots force slot reuse."""
+    d = tmp_path
+    cmd = [cli, "-in1", f"{G}/SeqPurge_in1.fastq.gz", f"{G}/SeqPurge_in7.fastq.gz", "-in2", f"{G}/SeqPurge_in2.fastq.gz", f"{G}/SeqPurge_in8.fastq.gz",
+           "-out1", str(d / "o1.fastq.gz"), "-out2", str(d / "o2.fastq.gz"), "-summary", str(d / "s.txt"), "-block_size", "333", "-block_prefetch", "2",
+           "-ncut", "0", "-qcut", "0", "-min_len", "15"]
+    subprocess.run(cmd, check=True)
+    want1 = _content(f"{G}/SeqPurge_out1.fastq.gz")
+    got1 = _content(d / "o1.fastq.gz")
+    assert got1.startswith(want1) and len(got1) > len(want1)
+
+
+def test_cli_header_mismatch_is_an_error(cli, tmp_path):
+    r = subprocess.run([cli, "-in1", f"{G}/SeqPurge_in1.fastq.gz", "-in2", f"{G}/SeqPurge_in4.fastq.gz", "-out1", str(tmp_path / "a.gz"), "-out2", str(tmp_path / "b.gz")],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "Headers of reads do not match" in r.stderr
