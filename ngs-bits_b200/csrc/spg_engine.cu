@@ -222,6 +222,7 @@ struct Slot
 	spg_result* h_res = nullptr;
 	spg_result* d_res = nullptr;
 	cudaEvent_t done = nullptr;
+	cudaStream_t stream = nullptr; // own stream: H2D / kernel / D2H of different slots of one device overlap
 	int state = SLOT_IDLE;
 	int n = 0;
 };
@@ -479,6 +480,7 @@ int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, i
 		CREATE_CUDA(cudaMalloc(&sl.d_block, ctx->block_bytes));
 		CREATE_CUDA(cudaMalloc(&sl.d_res, (size_t)cap * sizeof(spg_result)));
 		CREATE_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+		CREATE_CUDA(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
 		memset(sl.h_block, 0, ctx->block_bytes);
 	}
 #undef CREATE_CUDA
@@ -519,24 +521,24 @@ int spg_submit(spg_ctx* ctx, int slot, int n_pairs)
 		const size_t pb = ctx->plane_bytes;
 		if (n_pairs == ctx->max_pairs)
 		{
-			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block, sl.h_block, ctx->block_bytes, cudaMemcpyHostToDevice, d.stream));
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block, sl.h_block, ctx->block_bytes, cudaMemcpyHostToDevice, sl.stream));
 		}
 		else
 		{
-			for (int k = 0; k < 4; ++k) SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + k * pb, sl.h_block + k * pb, rows, cudaMemcpyHostToDevice, d.stream));
-			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb, sl.h_block + 4 * pb, lens, cudaMemcpyHostToDevice, d.stream));
-			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb + ctx->len_bytes, sl.h_block + 4 * pb + ctx->len_bytes, lens, cudaMemcpyHostToDevice, d.stream));
+			for (int k = 0; k < 4; ++k) SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + k * pb, sl.h_block + k * pb, rows, cudaMemcpyHostToDevice, sl.stream));
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb, sl.h_block + 4 * pb, lens, cudaMemcpyHostToDevice, sl.stream));
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb + ctx->len_bytes, sl.h_block + 4 * pb + ctx->len_bytes, lens, cudaMemcpyHostToDevice, sl.stream));
 		}
 		int rc = launch_trim(ctx, d, sl.d_block, sl.d_block + pb, sl.d_block + 2 * pb, sl.d_block + 3 * pb, reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb),
-		                     reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.d_res, d.stream);
+		                     reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.d_res, sl.stream);
 		if (rc != SPG_OK) return rc;
-		SPG_CUDA(ctx, cudaMemcpyAsync(sl.h_res, sl.d_res, (size_t)n_pairs * sizeof(spg_result), cudaMemcpyDeviceToHost, d.stream));
+		SPG_CUDA(ctx, cudaMemcpyAsync(sl.h_res, sl.d_res, (size_t)n_pairs * sizeof(spg_result), cudaMemcpyDeviceToHost, sl.stream));
 		if (ctx->params.ec) // edited rows come back in the slot
 		{
-			for (int k = 0; k < 4; ++k) SPG_CUDA(ctx, cudaMemcpyAsync(sl.h_block + k * pb, sl.d_block + k * pb, rows, cudaMemcpyDeviceToHost, d.stream));
+			for (int k = 0; k < 4; ++k) SPG_CUDA(ctx, cudaMemcpyAsync(sl.h_block + k * pb, sl.d_block + k * pb, rows, cudaMemcpyDeviceToHost, sl.stream));
 		}
 	}
-	SPG_CUDA(ctx, cudaEventRecord(sl.done, d.stream));
+	SPG_CUDA(ctx, cudaEventRecord(sl.done, sl.stream));
 	sl.state = SLOT_SUBMITTED;
 	return SPG_OK;
 }
@@ -606,6 +608,7 @@ void spg_destroy(spg_ctx* ctx)
 			cudaEventSynchronize(sl.done);
 			cudaEventDestroy(sl.done);
 		}
+		if (sl.stream) cudaStreamDestroy(sl.stream);
 		if (sl.h_block) cudaFreeHost(sl.h_block);
 		if (sl.h_res) cudaFreeHost(sl.h_res);
 		if (sl.d_block) cudaFree(sl.d_block);

@@ -566,8 +566,9 @@ __device__ __forceinline__ int step1_planes(const KArgs& A, const SmemTables& T,
 	uint32_t mw[NW];
 #pragma unroll
 	for (int w = 0; w < NW; ++w) mw[w] = low_bits(L - 32 * w - lane);
-	// survivors of the pre-filter are rare: remember them per round, evaluate them after the sweep
-	uint32_t surv[NW], cand[NW];
+	// survivors of the pre-filter are rare: every lane notes its own (bit q of smask) and the warp votes once after the sweep
+	uint32_t smask = 0;
+	int mmq[NW], totq[NW];
 #pragma unroll
 	for (int q = 0; q < NW; ++q)
 	{
@@ -585,28 +586,30 @@ __device__ __forceinline__ int step1_planes(const KArgs& A, const SmemTables& T,
 		}
 		const int o = 32 * q + lane;
 		const int tot = HASN ? nv : max(L - o, 0);
-		const int m = tot - mm;
-		surv[q] = __ballot_sync(kFull, o >= 1 && tot > 0 && m >= (int)T.mmin[tot]);
-		cand[q] = ((uint32_t)m << 16) | (uint32_t)mm;
+		mmq[q] = mm;
+		if (HASN) totq[q] = tot;
+		if (o >= 1 && tot > 0 && tot - mm >= (int)T.mmin[tot]) smask |= 1u << q;
 	}
+	if (!__any_sync(kFull, smask != 0)) return -1; // the common case for pairs without an insert match
 	uint32_t key = kNoKey; // warp-uniform
 #pragma unroll
 	for (int q = 0; q < NW; ++q)
 	{
-		uint32_t b = surv[q];
+		uint32_t b = __ballot_sync(kFull, (smask >> q) & 1u);
 		while (b)
 		{
 			const int src = __ffs(b) - 1;
 			b &= b - 1;
-			const uint32_t c = __shfl_sync(kFull, cand[q], src);
-			key = min(key, candidate_key_warp(A, P, 32 * q + src, (int)(c >> 16), (int)(c & 0xFFFFu), lane));
+			const int mm = __shfl_sync(kFull, mmq[q], src);
+			const int tot = HASN ? __shfl_sync(kFull, totq[q], src) : max(L - 32 * q - src, 0);
+			key = min(key, candidate_key_warp(A, P, 32 * q + src, tot - mm, mm, lane));
 		}
 	}
 	return key == kNoKey ? -1 : (int)(key & 0xFFFFu);
 }
 
 // steps 2/3 on forward planes (AnalysisWorker.cpp:307-353, :355-407): first offset at which the adapter matches.
-// sh/sl(/sn): forward planes of the read shifted by lane. One ballot per round of 32 offsets; the lowest set bit wins.
+// sh/sl(/sn): forward planes of the read shifted by lane. Each lane notes its passing rounds; one vote per read.
 template <int NW, bool HASN>
 __device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTables& T, const uint32_t (&sh)[NW], const uint32_t (&sl)[NW], const uint32_t (&sn)[NW],
                                                    int len, uint32_t ah, uint32_t al, uint32_t an, int lane)
@@ -614,8 +617,7 @@ __device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTab
 	const uint32_t amask = ((1u << A.a_size) - 1u) & ~an;
 	const int tot_full = __popc(amask);
 	const uint32_t pass_full = T.passA[tot_full];
-	uint32_t hit[NW];
-	uint32_t any = 0;
+	uint32_t pm = 0; // bit q: this lane's offset 32*q+lane passes
 #pragma unroll
 	for (int q = 0; q < NW; ++q)
 	{
@@ -634,15 +636,12 @@ __device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTab
 			const int tot = __popc(valid);
 			pass = cnt > 0 && ((T.passA[tot] >> (tot - __popc(x))) & 1u);
 		}
-		hit[q] = __ballot_sync(kFull, pass);
-		any |= hit[q];
+		if (pass) pm |= 1u << q;
 	}
-	if (any == 0) return -1; // the common case
-	int found = -1;
-#pragma unroll
-	for (int q = NW - 1; q >= 0; --q)
-		if (hit[q]) found = 32 * q + __ffs(hit[q]) - 1;
-	return found;
+	if (!__any_sync(kFull, pm != 0)) return -1; // the common case: one vote per read
+	// lowest passing offset over all lanes
+	const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane) : 0xFFFFFFFFu;
+	return (int)__reduce_min_sync(kFull, mine);
 }
 
 template <int NW, bool HASN>

@@ -81,6 +81,13 @@ def test_cli_multiple_input_files_and_small_prefetch(cli, tmp_path):
 
 
 def test_cli_header_mismatch_is_an_error(cli, tmp_path):
+    r = subprocess.run([cli, "-in1", f"{G}/SeqPurge_in1.fastq.gz", "-in2", f"{G}/SeqPurge_in4.fastq.gz", "-out1", str(tmp_path / "a.gz"), "-out2", str(tmp_path / "b.gz"),
+                        "-block_size", "100"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Headers of reads do not match" in r.stderr
+
+
+def test_cli_unequal_entry_counts_is_an_error(cli, tmp_path):
+    """InputWorker.cpp:39-46: one stream ends before the other."""
     r = subprocess.run([cli, "-in1", f"{G}/SeqPurge_in1.fastq.gz", "-in2", f"{G}/SeqPurge_in4.fastq.gz", "-out1", str(tmp_path / "a.gz"), "-out2", str(tmp_path / "b.gz")],
                        capture_output=True, text=True)
-    assert r.returncode == 1 and "Headers of reads do not match" in r.stderr
+    assert r.returncode == 1 and "has more entries than" in r.stderr
