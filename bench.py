@@ -8,7 +8,7 @@ so ranks shard the stream with no collective on the data path: weak scaling).
 
 One "step" = one pass of the trimming hot path over one batch of `--pairs-per-step` synthetic pairs (BASELINE config 2:
 2x150 bp, insert ~ N(250,80), default Illumina adapters, defaults of SeqPurge: -qcut 15 -ncut 7). The batches are generated on the
-device and stay resident in HBM (a pool of `--pool` distinct batches, 6.4 GB each at the default size, so every launch reads
+device and stay resident in HBM (a pool of `--pool` distinct batches, 6.0 GB each at the default size, so every launch reads
 inputs far larger than the 126 MB L2).  Reported:
   value     whole-job Mpairs/s, inputs resident in HBM (kernel launches only), max over ranks of CUDA-event time
   e2e       same metric through the C ABI with HOST buffers: pinned slot -> H2D -> kernel -> D2H of the result records (spg_submit/spg_wait)
@@ -30,7 +30,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "Mread-pairs/s trimmed, 2x150bp synthetic"
 UNIT = "Mpairs/s"
 READ_LEN = 150
-STRIDE = 160
+STRIDE = 150  # row stride of the SoA planes: read length rounded up to an even number
 B_ALG = 2 * (READ_LEN + READ_LEN) + 8  # algorithmic bytes per pair
 WORKLOAD = "C2: synthetic 2x150bp pairs, insert~N(250,80), 0.1% substitutions, default Illumina adapters, SeqPurge defaults (-qcut 15 -ncut 7)"
 
@@ -324,7 +324,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_step": B, "resident_batches": pool_n, "read_len": READ_LEN, "row_stride": STRIDE,
-                   "l2": "inputs larger than L2 (each step reads a distinct 6.4 GB batch at the default size)", "parallelism": f"replicated engine x{world}, stream sharded by rank, no collective",
+                   "l2": "inputs larger than L2 (each step reads a distinct 6.0 GB batch at the default size)", "parallelism": f"replicated engine x{world}, stream sharded by rank, no collective",
                    "insert_hit_fraction": frac_insert},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_pair": B_ALG, "kernel_ms_mean": mean_kernel_ms, "kernel": "spg::trim_kernel<NW=5,CW=8,MINB=3>",

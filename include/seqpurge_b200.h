@@ -84,7 +84,7 @@ typedef struct spg_slot_view
 	uint8_t* quals2;
 	uint16_t* len1;  /* bases1/quals1 row length (the reference assumes |bases|==|qualities|) */
 	uint16_t* len2;
-	int32_t stride;    /* bytes per row, multiple of 16, >= max_len */
+	int32_t stride;    /* bytes per row: max_len rounded up to an even number (>= 16) */
 	int32_t max_pairs; /* capacity (the reference's -block_size) */
 } spg_slot_view;
 
@@ -117,7 +117,7 @@ int spg_submit(spg_ctx* ctx, int slot, int n_pairs);
 int spg_wait(spg_ctx* ctx, int slot, const spg_result** results);
 
 /* Device-resident form of the same operation (no copies): all pointers are device pointers on device_ids[device_index],
-   16-byte aligned; len arrays must be readable up to a multiple of 8 entries; stride a multiple of 16.
+   16-byte aligned; row planes and len arrays must be readable up to a multiple of 8 rows / entries; stride even, 16..1008.
    cuda_stream is a cudaStream_t (NULL = default stream). With -ec the row planes are edited in place. */
 int spg_trim_device(spg_ctx* ctx, int device_index, void* bases1, void* quals1, void* bases2, void* quals2, const uint16_t* len1, const uint16_t* len2,
                     int stride, int64_t n_pairs, spg_result* results, void* cuda_stream);

@@ -278,9 +278,9 @@ void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 {
 	int tp = (int)(24576 / (4 * (size_t)stride + 4)) / 8 * 8;
 	if (tp < 8) tp = 8;
-	if (tp > 64) tp = 64;
+	if (tp > 32) tp = 32; // sweeps: 32 pairs per tile is the sweet spot (larger tiles lower occupancy through shared memory)
 	tile_pairs = tp;
-	stages = 3;
+	stages = 2;
 	smem = (size_t)stages * (4 * (size_t)tp * stride + 4 * (size_t)tp);
 }
 
@@ -427,7 +427,7 @@ int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, i
 	}
 	ctx->max_pairs = max_pairs;
 	ctx->max_len = max_len;
-	ctx->stride = n_slots > 0 ? (max_len + 15) / 16 * 16 : 0;
+	ctx->stride = n_slots > 0 ? std::max(16, (max_len + 1) / 2 * 2) : 0; // even: a tile of 8 rows is then a multiple of 16 bytes (TMA)
 	const int cap = (max_pairs + 7) / 8 * 8;
 	ctx->plane_bytes = (size_t)cap * ctx->stride;
 	ctx->len_bytes = (size_t)cap * sizeof(uint16_t);
@@ -560,7 +560,7 @@ int spg_trim_device(spg_ctx* ctx, int device_index, void* bases1, void* quals1, 
 {
 	if (!ctx) return SPG_ERR_PARAM;
 	if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SPG_ERR_PARAM, "device index out of range");
-	if (stride < 16 || stride % 16 != 0 || stride > 1008) return fail(ctx, SPG_ERR_PARAM, "stride must be a multiple of 16 in [16,1008]");
+	if (stride < 16 || stride % 2 != 0 || stride > 1008) return fail(ctx, SPG_ERR_PARAM, "stride must be even and in [16,1008]");
 	const uintptr_t bits = (uintptr_t)bases1 | (uintptr_t)quals1 | (uintptr_t)bases2 | (uintptr_t)quals2 | (uintptr_t)len1 | (uintptr_t)len2;
 	if (bits & 15u) return fail(ctx, SPG_ERR_PARAM, "device pointers must be 16-byte aligned");
 	if ((uintptr_t)results & 7u) return fail(ctx, SPG_ERR_PARAM, "results must be 8-byte aligned");

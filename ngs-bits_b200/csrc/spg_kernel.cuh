@@ -867,7 +867,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 				}
 				const long long first = t * TP;
 				const int cnt = (int)min((long long)TP, A.n_pairs - first);
-				const uint32_t row_bytes = (uint32_t)cnt * (uint32_t)A.stride;
+				// bulk copies move multiples of 16 bytes: a ragged last tile (cnt not a multiple of 8) reads up to 14 bytes past its
+				// last row, which stay inside the row planes (they are allocated in multiples of 8 rows)
+				const uint32_t row_bytes = ((uint32_t)cnt * (uint32_t)A.stride + 15u) & ~15u;
 				const uint32_t len_bytes = (uint32_t)((cnt + 7) / 8) * 16u;
 				const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 				mbar_arrive_expect_tx(&full_bar[s], 4 * row_bytes + 2 * len_bytes);
@@ -910,17 +912,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 				P.len2 = (int)lds_u16(lens + 2u * (uint32_t)(TP + pr));
 				bool edited = false;
 				process_pair<NW>(A, T, P, lane, A.out + first + pr, edited);
-				if (edited) // -ec: write the edited rows back (16-byte vectors; rows are 16-byte aligned)
+				if (edited) // -ec: write the edited rows back
 				{
 					__syncwarp();
 					const size_t goff = (size_t)(first + pr) * A.stride;
-					const int vecs = A.stride / 16;
-					for (int v = lane; v < vecs; v += 32)
+					const int halves = A.stride / 2; // rows are 2-byte aligned (stride is even)
+					for (int v = lane; v < halves; v += 32)
 					{
-						reinterpret_cast<uint4*>(A.b1 + goff)[v] = lds_v4(P.r1 + 16u * v);
-						reinterpret_cast<uint4*>(A.q1 + goff)[v] = lds_v4(P.q1 + 16u * v);
-						reinterpret_cast<uint4*>(A.b2 + goff)[v] = lds_v4(P.r2 + 16u * v);
-						reinterpret_cast<uint4*>(A.q2 + goff)[v] = lds_v4(P.q2 + 16u * v);
+						reinterpret_cast<uint16_t*>(A.b1 + goff)[v] = (uint16_t)lds_u16(P.r1 + 2u * v);
+						reinterpret_cast<uint16_t*>(A.q1 + goff)[v] = (uint16_t)lds_u16(P.q1 + 2u * v);
+						reinterpret_cast<uint16_t*>(A.b2 + goff)[v] = (uint16_t)lds_u16(P.r2 + 2u * v);
+						reinterpret_cast<uint16_t*>(A.q2 + goff)[v] = (uint16_t)lds_u16(P.q2 + 2u * v);
 					}
 				}
 			}

@@ -136,6 +136,21 @@ def test_random_batches(sp, L, seed):
     assert (want["flags"] & 1).sum() > 100 and (want["flags"] & 2).sum() > 10  # both trimming modes exercised
 
 
+@pytest.mark.parametrize("L,stride,n", [(150, 150, 1003), (101, 102, 77), (250, 250, 2001), (36, 36, 9)])
+def test_tight_even_strides_and_ragged_last_tile(sp, L, stride, n):
+    """Rows packed at an even stride that is not a multiple of 16, pair counts that are not a multiple of the tile size
+    (the last TMA tile is ragged), with -ec so that the edited rows travel back as well."""
+    batch = H.random_batch(n, L, 100 + L, error_rate=0.03, n_rate=0.002, lowq_tail=6.0, stride=stride)
+    ref = batch.copy()
+    want, want_ec = H.oracle_trim(ref, ec=True)
+    got, edited, got_ec = gpu_trim(sp, batch, ec=True)
+    assert_same(got, want, batch)
+    for name in ("bases1", "quals1", "bases2", "quals2"):
+        assert np.array_equal(getattr(edited, name)[:n], getattr(ref, name)[:n]), name
+    for k in want_ec:
+        assert np.array_equal(got_ec[k], want_ec[k]), k
+
+
 def test_random_ragged_lengths_and_n_runs(sp):
     """len1 != len2, zero-length reads, injected N runs, -ncut/-qcut on (appendix B)."""
     batch = H.random_batch(4000, 150, 11, ragged=True, n_runs=0.2, n_rate=0.01, lowq_tail=20.0)
