@@ -357,6 +357,20 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	adapter_planes(ctx->a1.data(), ctx->a_size, a.a1h, a.a1l, a.a1n);
 	adapter_planes(ctx->a2.data(), ctx->a_size, a.a2h, a.a2l, a.a2n);
 	memcpy(a.passA, ctx->tables.passA, sizeof(a.passA));
+	{
+		const uint32_t full = (ctx->a_size >= 32) ? 0xffffffffu : ((1u << ctx->a_size) - 1u);
+		a.a1mask = full & ~a.a1n;
+		a.a2mask = full & ~a.a2n;
+		auto by_mm = [&](uint32_t mask) {
+			const int tot = __builtin_popcount(mask);
+			uint32_t bits = 0;
+			for (int mm = 0; mm <= tot; ++mm)
+				if ((ctx->tables.passA[tot] >> (tot - mm)) & 1u) bits |= 1u << mm;
+			return bits;
+		};
+		a.a1pass = by_mm(a.a1mask);
+		a.a2pass = by_mm(a.a2mask);
+	}
 	memset(a.a1, 'N', sizeof(a.a1)); // never read beyond the adapter length: a_size, adapter_overlap <= min(|a1|,|a2|,32)
 	memset(a.a2, 'N', sizeof(a.a2));
 	memcpy(a.a1, ctx->a1.data(), std::min<size_t>(32, ctx->a1.size()));

@@ -63,6 +63,8 @@ struct KArgs
 	int force_bytewise;
 	uint32_t a1h, a1l, a1n; // planes of the first a_size adapter bases
 	uint32_t a2h, a2l, a2n;
+	uint32_t a1mask, a2mask; // adapter positions < a_size that are not N
+	uint32_t a1pass, a2pass; // bit j: a full-window comparison (all of amask) with j mismatches passes
 	uint32_t passA[21]; // [T] bit m: adapter-only hit with m matches out of T compared bases passes (steps 2/3)
 	uint8_t a1[32];     // adapter bytes (first 32)
 	uint8_t a2[32];
@@ -240,8 +242,9 @@ __device__ __noinline__ int trim_quality_slow(const KArgs& A, uint32_t q, int co
 	return found < 0 ? -1 : found + window;
 }
 
-// returns the new length of the read (== count if nothing is trimmed)
-__device__ __forceinline__ int trim_quality_warp(const KArgs& A, uint32_t q, int count, int lane)
+// the complete algorithm for any position of the trimming point (window <= 32 by warp scans, else one window start per lane);
+// returns the new length of the read
+__device__ __noinline__ int trim_quality_general(const KArgs& A, uint32_t q, int count, int lane)
 {
 	const int window = A.qwin;
 	if (count < window) return count;
@@ -287,6 +290,32 @@ __device__ __forceinline__ int trim_quality_warp(const KArgs& A, uint32_t q, int
 		break;
 	}
 	return max(count_new, 0);
+}
+
+// Common case inline: the trimming point lies within the last 32 bases of the read. One load per lane (q[count-32+lane]) serves
+// both the window search (warp scan) and the removal of the trailing low-quality bases (bit tricks on one ballot); anything
+// else goes to trim_quality_general. Returns the new length of the read (== count if nothing is trimmed).
+__device__ __forceinline__ int trim_quality_warp(const KArgs& A, uint32_t q, int count, int lane)
+{
+	const int window = A.qwin;
+	if (count < window) return count;
+	if (window > 32) return trim_quality_general(A, q, count, lane);
+	const int base = count - 32;
+	const int i = base + lane;
+	int v = 0;
+	if (i >= 0) v = qual_at(q, i, A.qoff);
+	int p = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+		asm volatile("{\n\t.reg .pred g;\n\t.reg .s32 t;\n\tshfl.sync.up.b32 t|g, %0, %1, 0, 0xffffffff;\n\t@g add.s32 %0, %0, t;\n\t}" : "+r"(p) : "r"(d));
+	const int s = __shfl_sync(kFull, p, lane + window - 1) - p + v;
+	const uint32_t okm = __ballot_sync(kFull, i >= 0 && lane <= 32 - window && s >= A.qthr);
+	const uint32_t low = __ballot_sync(kFull, i >= 0 && v < A.qcut); // bit l: position base+l is below the cutoff
+	if (okm == 0) return trim_quality_general(A, q, count, lane);     // trimming point further left (or nowhere): rare
+	const int t = 31 - __clz(okm) + window - 1;                       // lane of the last base of the highest passing window
+	const uint32_t x = ~low << (31 - t);                              // bit 31 = "base at lane t is not low", then downwards
+	if (x == 0) return trim_quality_general(A, q, count, lane);       // low bases all the way to the start of this block: rare
+	return base + t + 1 - __clz(x);
 }
 
 // ---- FastqEntry::trimN (src/cppNGS/FastqFileStream.cpp:89-117), warp-parallel over run starts; only reads that hold an N get here ----------
@@ -612,31 +641,28 @@ __device__ __forceinline__ int step1_planes(const KArgs& A, const SmemTables& T,
 // sh/sl(/sn): forward planes of the read shifted by lane. Each lane notes its passing rounds; one vote per read.
 template <int NW, bool HASN>
 __device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTables& T, const uint32_t (&sh)[NW], const uint32_t (&sl)[NW], const uint32_t (&sn)[NW],
-                                                   int len, uint32_t ah, uint32_t al, uint32_t an, int lane)
+                                                   int len, uint32_t ah, uint32_t al, uint32_t an, uint32_t amask, uint32_t pass_by_mm, int lane)
 {
-	const uint32_t amask = ((1u << A.a_size) - 1u) & ~an;
-	const int tot_full = __popc(amask);
-	const uint32_t pass_full = T.passA[tot_full];
-	uint32_t pm = 0; // bit q: this lane's offset 32*q+lane passes
+	// amask: the a_size adapter positions that are not N; pass_by_mm: bit j set = a full window with j mismatches passes
+	// (both host-built, KArgs). Bit q of pm: this lane's offset 32*q+lane passes.
+	uint32_t pm = 0;
 #pragma unroll
-	for (int q = 0; q < NW; ++q)
+	for (int q = NW - 1; q >= 0; --q)
 	{
-		bool pass;
+		uint32_t bit;
 		if (!HASN && 32 * q + 31 + A.a_size <= len) // warp-uniform: every lane has the full adapter window inside the read
 		{
-			const uint32_t x = ((sh[q] ^ ah) | (sl[q] ^ al)) & amask;
-			pass = (pass_full >> (tot_full - __popc(x))) & 1u;
+			bit = pass_by_mm >> __popc(((sh[q] ^ ah) | (sl[q] ^ al)) & amask);
 		}
 		else
 		{
 			const int cnt = min(A.a_size, len - 32 * q - lane); // compared bases (the read end cuts the window); <= 0: none
 			uint32_t valid = low_bits(cnt) & ~an;
 			if (HASN) valid &= ~sn[q];
-			const uint32_t x = ((sh[q] ^ ah) | (sl[q] ^ al)) & valid;
 			const int tot = __popc(valid);
-			pass = cnt > 0 && ((T.passA[tot] >> (tot - __popc(x))) & 1u);
+			bit = cnt > 0 ? T.passA[tot] >> (tot - __popc(((sh[q] ^ ah) | (sl[q] ^ al)) & valid)) : 0u;
 		}
-		if (pass) pm |= 1u << q;
+		pm = pm * 2u + (bit & 1u);
 	}
 	if (!__any_sync(kFull, pm != 0)) return -1; // the common case: one vote per read
 	// lowest passing offset over all lanes
@@ -663,11 +689,11 @@ __device__ __forceinline__ Step123 steps_planes(const KArgs& A, const SmemTables
 		shift_words<NW>(f1.h, lane, sh);
 		shift_words<NW>(f1.l, lane, sl);
 		if (HASN) shift_words<NW>(n1, lane, sn);
-		r.fwd = adapter_scan_planes<NW, HASN>(A, T, sh, sl, sn, P.len1, A.a1h, A.a1l, A.a1n, lane);
+		r.fwd = adapter_scan_planes<NW, HASN>(A, T, sh, sl, sn, P.len1, A.a1h, A.a1l, A.a1n, A.a1mask, A.a1pass, lane);
 		shift_words<NW>(f2.h, lane, sh);
 		shift_words<NW>(f2.l, lane, sl);
 		if (HASN) shift_words<NW>(n2, lane, sn);
-		r.rev = adapter_scan_planes<NW, HASN>(A, T, sh, sl, sn, P.len2, A.a2h, A.a2l, A.a2n, lane);
+		r.rev = adapter_scan_planes<NW, HASN>(A, T, sh, sl, sn, P.len2, A.a2h, A.a2l, A.a2n, A.a2mask, A.a2pass, lane);
 	}
 	return r;
 }
