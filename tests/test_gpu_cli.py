@@ -91,3 +91,38 @@ def test_cli_unequal_entry_counts_is_an_error(cli, tmp_path):
     r = subprocess.run([cli, "-in1", f"{G}/SeqPurge_in1.fastq.gz", "-in2", f"{G}/SeqPurge_in4.fastq.gz", "-out1", str(tmp_path / "a.gz"), "-out2", str(tmp_path / "b.gz")],
                        capture_output=True, text=True)
     assert r.returncode == 1 and "has more entries than" in r.stderr
+
+
+def test_cli_config1_synthetic_10k_gz_byte_identical(cli, oracle_build, tmp_path):
+    """BASELINE config 1: 10 k synthetic 2x150 pairs (device generator), default adapters, FASTQ.gz in -> trimmed FASTQ.gz out;
+    output files byte-identical to the CPU oracle run with -threads 1, also with two blocks in flight per slot ring."""
+    import gzip as gz
+
+    import numpy as np
+    import torch
+
+    import seqpurge_b200 as sp
+
+    n, L = 10_000, 150
+    dev = torch.device("cuda:0")
+    t = {k: torch.empty((n, L), dtype=torch.uint8, device=dev) for k in ("bases1", "quals1", "bases2", "quals2")}
+    l1 = torch.empty(n, dtype=torch.int16, device=dev)
+    l2 = torch.empty(n, dtype=torch.int16, device=dev)
+    sp.synth_device(sp.SynthConfig(read_len=L, error_rate=0.001, lowq_tail_mean=3.0), 0, n, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
+    torch.cuda.synchronize()
+    host = {k: v.cpu().numpy() for k, v in t.items()}
+    for r, (bk, qk) in enumerate((("bases1", "quals1"), ("bases2", "quals2")), start=1):
+        with gz.open(tmp_path / f"in{r}.fastq.gz", "wb", compresslevel=1) as f:
+            for i in range(n):
+                f.write(b"@SIM:1:B200:1:%d:%d %d:N:0:ACGT\n" % (i // 1000, i, r))
+                f.write(host[bk][i].tobytes() + b"\n+\n" + host[qk][i].tobytes() + b"\n")
+    outs = {}
+    for tool, exe, extra in (("gpu", cli, ["-block_size", "1500", "-block_prefetch", "3"]), ("oracle", os.path.join(oracle_build, "seqpurge_oracle"), ["-threads", "1"])):
+        d = tmp_path / tool
+        d.mkdir()
+        subprocess.run([exe, "-in1", str(tmp_path / "in1.fastq.gz"), "-in2", str(tmp_path / "in2.fastq.gz"), "-out1", str(d / "o1.fastq.gz"), "-out2", str(d / "o2.fastq.gz"),
+                        "-out3", str(d / "single"), "-summary", str(d / "s.txt")] + extra, check=True)
+        outs[tool] = d
+    for name in ("o1.fastq.gz", "o2.fastq.gz", "single_R1.fastq.gz", "single_R2.fastq.gz"):
+        assert _raw(outs["gpu"] / name) == _raw(outs["oracle"] / name), name
+    assert len(_content(outs["gpu"] / "o1.fastq.gz")) > 1_000_000

@@ -5,6 +5,8 @@ Inputs: the reference's own SeqPurge fixtures (tests/golden, flags of src/tools-
 batches covering the edge cases of SURVEY.md appendix B (unequal and zero lengths, N runs, low-quality tails, overlaps > 170 bases,
 bytes outside ACGTN, reads of up to 999 bases), and device-generated synthetic batches of the BASELINE configs.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -270,3 +272,71 @@ def test_device_synthetic_configs(sp, name):
         assert_same(got, want, batch)
         assert (want["status"] == 0).all()
     eng.close()
+
+
+def test_full_size_config2_properties(sp):
+    """BASELINE config 2 at its full size (100 M synthetic 2x150 pairs, 10 resident batches of 10 M): properties that do not need the
+    oracle on every pair -- the bit-plane path and the byte-wise path (two independent device implementations of the specification)
+    agree on a checksum of checksums, the result is deterministic, every record satisfies the invariants of the trimming rules -- plus
+    the oracle on random 50 k-pair slices of every batch."""
+    import torch
+
+    total = int(os.environ.get("SPG_FULL_SIZE_PAIRS", "100000000"))
+    nb = 10
+    n = total // nb // 8 * 8
+    L, stride = 150, 150
+    dev = torch.device("cuda:0")
+    free, _ = torch.cuda.mem_get_info()
+    if free < nb * n * (4 * stride + 4) + 4 * n * 8 + (2 << 30):
+        pytest.skip("not enough free device memory for the full-size config")
+    cfg = sp.SynthConfig(read_len=L)
+    eng = sp.Engine(sp.TrimmingParameters(), devices=(0,))
+    rng = np.random.default_rng(7)
+    res = torch.empty((n, 8), dtype=torch.uint8, device=dev)
+    res2 = torch.empty((n, 8), dtype=torch.uint8, device=dev)
+    sums_planes, sums_bytes = [], []
+    for b in range(nb):
+        t = {k: torch.empty((n, stride), dtype=torch.uint8, device=dev) for k in ("bases1", "quals1", "bases2", "quals2")}
+        l1 = torch.empty(n, dtype=torch.int16, device=dev)
+        l2 = torch.empty(n, dtype=torch.int16, device=dev)
+        sp.synth_device(cfg, b * n, n, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
+        eng.set_option(sp.OPT_FORCE_BYTEWISE, 0)
+        eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, res)
+        eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, res2)
+        torch.cuda.synchronize()
+        assert torch.equal(res, res2), "two runs over the same batch differ"
+        w = res.view(torch.int64).view(-1)
+        sums_planes.append(int((w * (torch.arange(n, device=dev) % 1000003 + 1)).sum().item()))
+        # invariants of the trimming rules on every record
+        len1 = (w & 0xFFFF)
+        len2 = ((w >> 16) & 0xFFFF)
+        off = ((w >> 32) & 0xFFFF)
+        flags = ((w >> 48) & 0xFF)
+        status = ((w >> 56) & 0xFF)
+        assert int(status.max().item()) == 0
+        assert int(len1.max().item()) <= L and int(len2.max().item()) <= L
+        ins = (flags & 1) != 0
+        assert bool(((off == 0xFFFF) == ~ins).all()), "best_offset set iff insert flag"
+        assert bool((len1[ins] <= L - off[ins]).all()) and bool((len2[ins] <= L - off[ins]).all())
+        assert bool(((flags & 3) != 3).all()), "insert and adapter-only trimming are exclusive"
+        frac = float(ins.float().mean().item())
+        assert 0.05 < frac < 0.2  # inserts ~ N(250,80): about 10 % are shorter than the read
+        # the byte-wise device path on the same batch
+        eng.set_option(sp.OPT_FORCE_BYTEWISE, 1)
+        eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, res2)
+        torch.cuda.synchronize()
+        w2 = res2.view(torch.int64).view(-1)
+        sums_bytes.append(int((w2 * (torch.arange(n, device=dev) % 1000003 + 1)).sum().item()))
+        # the oracle on a random slice
+        m = 50_000
+        st = int(rng.integers(0, n - m)) // 8 * 8
+        batch = H.Batch(m, stride)
+        for k in t:
+            getattr(batch, k)[:m] = t[k][st : st + m].cpu().numpy()
+        batch.len1[:m] = l1[st : st + m].cpu().numpy().view(np.uint16)
+        batch.len2[:m] = l2[st : st + m].cpu().numpy().view(np.uint16)
+        want, _ = H.oracle_trim(batch, threads=8)
+        assert_same(sp.results_from_tensor(res[st : st + m]), want, batch)
+        del t, l1, l2
+    eng.close()
+    assert sums_planes == sums_bytes, "plane path and byte-wise path disagree"
