@@ -141,6 +141,7 @@ struct SmemTables
 {
 	uint16_t mmin[SPG_MAXLEN];
 	uint32_t passA[21];
+	uint32_t passM[21]; // the same by mismatches: [T] bit j: j mismatches out of T compared bases pass
 };
 
 __device__ __forceinline__ bool is_acgtn(uint32_t c)
@@ -503,16 +504,19 @@ struct Planes
 	uint32_t h[NW], l[NW];
 };
 
-// forward planes of one read; returns (per lane) whether one of its bytes is not A/C/G/T
+// forward planes of one read; returns (per lane) whether one of its bytes is not A/C/G/T.
+// D = 0: left aligned (bit b of word w is position 32*w+b). D = 32*NW-len: right aligned (position p sits at bit p+D, the read
+// ends at the top of the last word) -- used for read 2, see planes_revcomp_shifted and adapter_scan_right.
 template <int NW>
-__device__ __forceinline__ bool pack_forward(uint32_t row, int len, int lane, Planes<NW>& pl)
+__device__ __forceinline__ bool pack_forward(uint32_t row, int len, int D, int lane, Planes<NW>& pl)
 {
 	bool bad = false;
 #pragma unroll
 	for (int w = 0; w < NW; ++w)
 	{
 		uint32_t c = 'A';
-		if (32 * w + lane < len) c = lds_u8(row + 32 * w + lane);
+		const int pos = 32 * w + lane - D;
+		if ((unsigned)pos < (unsigned)len) c = lds_u8(row + pos);
 		pl.h[w] = __ballot_sync(kFull, c & 4u);
 		pl.l[w] = __ballot_sync(kFull, c & 2u);
 		// a byte is A/C/G/T iff it equals the letter its own 2-bit code stands for
@@ -521,16 +525,18 @@ __device__ __forceinline__ bool pack_forward(uint32_t row, int len, int lane, Pl
 	return bad;
 }
 
-// N plane of one read and whether it holds bytes outside ACGTN (only for pairs in which pack_forward saw something unusual)
+// N plane of one read (same alignment rule as pack_forward) and whether it holds bytes outside ACGTN (only for pairs in which
+// pack_forward saw something unusual)
 template <int NW>
-__device__ __forceinline__ void pack_special(uint32_t row, int len, int lane, uint32_t (&n)[NW], bool& hasN, bool& other)
+__device__ __forceinline__ void pack_special(uint32_t row, int len, int D, int lane, uint32_t (&n)[NW], bool& hasN, bool& other)
 {
 	uint32_t anyN = 0, anyOther = 0;
 #pragma unroll
 	for (int w = 0; w < NW; ++w)
 	{
 		uint32_t c = 'A';
-		if (32 * w + lane < len) c = lds_u8(row + 32 * w + lane);
+		const int pos = 32 * w + lane - D;
+		if ((unsigned)pos < (unsigned)len) c = lds_u8(row + pos);
 		n[w] = __ballot_sync(kFull, c == 'N');
 		anyN |= n[w];
 		anyOther |= __ballot_sync(kFull, !is_acgtn(c));
@@ -539,20 +545,20 @@ __device__ __forceinline__ void pack_special(uint32_t row, int len, int lane, ui
 	other = anyOther != 0;
 }
 
-// planes of revcomp(read 2), i.e. position j holds complement(R2[len-1-j]), already shifted right by `lane` bits:
-// word w holds positions 32*w+lane .. 32*w+lane+31. Lane l owns every offset o = 32*q + l, so these NW words are all the
-// windows of revcomp(read 2) it ever needs.
+// Planes of revcomp(read 2) from the RIGHT-ALIGNED forward planes of read 2, without touching the bytes again: reversing the
+// whole NW*32-bit string (word order + BREV) puts complement-position j = len-1-p at bit j exactly because the read ends at the
+// top bit; the complement flips the hi plane. Returned already shifted right by `lane` bits: word w holds positions 32*w+lane ..
+// 32*w+lane+31 -- lane l owns every offset o = 32*q + l, so these NW words are all the windows of revcomp(read 2) it ever needs.
+// Positions >= len hold padding (hi plane 1): they are never compared (masks of step 1 stop at min(len1,len2)).
 template <int NW>
-__device__ __forceinline__ void pack_revcomp_shifted(uint32_t row, int len, int lane, Planes<NW>& s)
+__device__ __forceinline__ void planes_revcomp_shifted(const Planes<NW>& f2r, int lane, Planes<NW>& s)
 {
 	uint32_t h[NW], l[NW];
 #pragma unroll
 	for (int w = 0; w < NW; ++w)
 	{
-		uint32_t c = 'T';
-		if (32 * w + lane < len) c = lds_u8(row + len - 1 - 32 * w - lane);
-		h[w] = __ballot_sync(kFull, !(c & 4u));
-		l[w] = __ballot_sync(kFull, c & 2u);
+		h[w] = ~__brev(f2r.h[NW - 1 - w]);
+		l[w] = __brev(f2r.l[NW - 1 - w]);
 	}
 #pragma unroll
 	for (int w = 0; w < NW; ++w)
@@ -562,16 +568,11 @@ __device__ __forceinline__ void pack_revcomp_shifted(uint32_t row, int len, int 
 	}
 }
 template <int NW>
-__device__ __forceinline__ void revcomp_n_shifted(uint32_t row, int len, int lane, uint32_t (&sn)[NW])
+__device__ __forceinline__ void n_revcomp_shifted(const uint32_t (&n2r)[NW], int lane, uint32_t (&sn)[NW])
 {
 	uint32_t n[NW];
 #pragma unroll
-	for (int w = 0; w < NW; ++w)
-	{
-		uint32_t c = 'T';
-		if (32 * w + lane < len) c = lds_u8(row + len - 1 - 32 * w - lane);
-		n[w] = __ballot_sync(kFull, c == 'N');
-	}
+	for (int w = 0; w < NW; ++w) n[w] = __brev(n2r[NW - 1 - w]);
 #pragma unroll
 	for (int w = 0; w < NW; ++w) sn[w] = __funnelshift_r(n[w], (w + 1 < NW) ? n[w + 1] : 0u, lane);
 }
@@ -670,17 +671,47 @@ __device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTab
 	return (int)__reduce_min_sync(kFull, mine);
 }
 
+// step 3 on the RIGHT-ALIGNED forward planes of read 2 (shifted by lane): offset o sits at bit k = o + D, the read ends at bit
+// 32*NW, so which rounds see the full adapter window is known at compile time (all but the last) and the last round's window
+// length min(a_size, 32-lane) does not depend on the read at all. No warp-uniform branches, one vote.
 template <int NW, bool HASN>
-__device__ __forceinline__ Step123 steps_planes(const KArgs& A, const SmemTables& T, const Pair& P, const Planes<NW>& f1, const Planes<NW>& f2,
-                                                const uint32_t (&n1)[NW], const uint32_t (&n2)[NW], int lane)
+__device__ __forceinline__ int adapter_scan_right(const KArgs& A, const SmemTables& T, const uint32_t (&sh)[NW], const uint32_t (&sl)[NW], const uint32_t (&sn)[NW],
+                                                  int D, uint32_t ah, uint32_t al, uint32_t an, uint32_t amask, uint32_t pass_by_mm, int lane)
+{
+	uint32_t pm = 0;
+#pragma unroll
+	for (int q = NW - 1; q >= 0; --q)
+	{
+		uint32_t bit;
+		const uint32_t x = (sh[q] ^ ah) | (sl[q] ^ al);
+		if (q < NW - 1 && !HASN) bit = pass_by_mm >> __popc(x & amask);
+		else
+		{
+			uint32_t valid = (q < NW - 1) ? amask : (low_bits(min(A.a_size, 32 - lane)) & ~an);
+			if (HASN) valid &= ~sn[q];
+			bit = T.passM[__popc(valid)] >> __popc(x & valid);
+		}
+		pm = pm * 2u + (bit & 1u);
+	}
+	// bits k < D are padding in front of the read: drop the rounds that start there (32*q + lane < D)
+	pm &= ~low_bits((D - lane + 31) >> 5);
+	if (!__any_sync(kFull, pm != 0)) return -1;
+	const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane - D) : 0xFFFFFFFFu;
+	return (int)__reduce_min_sync(kFull, mine);
+}
+
+// f1: forward planes of read 1 (left aligned); f2r: forward planes of read 2, right aligned by D2 = 32*NW - len2.
+template <int NW, bool HASN>
+__device__ __forceinline__ Step123 steps_planes(const KArgs& A, const SmemTables& T, const Pair& P, const Planes<NW>& f1, const Planes<NW>& f2r, int D2,
+                                                const uint32_t (&n1)[NW], const uint32_t (&n2r)[NW], int lane)
 {
 	Step123 r;
 	r.fwd = r.rev = -1;
 	{
 		Planes<NW> s2s;
 		uint32_t n2s[NW];
-		pack_revcomp_shifted<NW>(P.r2, P.len2, lane, s2s);
-		if (HASN) revcomp_n_shifted<NW>(P.r2, P.len2, lane, n2s);
+		planes_revcomp_shifted<NW>(f2r, lane, s2s);
+		if (HASN) n_revcomp_shifted<NW>(n2r, lane, n2s);
 		r.best_offset = step1_planes<NW, HASN>(A, T, P, f1, s2s, n1, n2s, lane);
 	}
 	if (r.best_offset < 0)
@@ -690,10 +721,10 @@ __device__ __forceinline__ Step123 steps_planes(const KArgs& A, const SmemTables
 		shift_words<NW>(f1.l, lane, sl);
 		if (HASN) shift_words<NW>(n1, lane, sn);
 		r.fwd = adapter_scan_planes<NW, HASN>(A, T, sh, sl, sn, P.len1, A.a1h, A.a1l, A.a1n, A.a1mask, A.a1pass, lane);
-		shift_words<NW>(f2.h, lane, sh);
-		shift_words<NW>(f2.l, lane, sl);
-		if (HASN) shift_words<NW>(n2, lane, sn);
-		r.rev = adapter_scan_planes<NW, HASN>(A, T, sh, sl, sn, P.len2, A.a2h, A.a2l, A.a2n, A.a2mask, A.a2pass, lane);
+		shift_words<NW>(f2r.h, lane, sh);
+		shift_words<NW>(f2r.l, lane, sl);
+		if (HASN) shift_words<NW>(n2r, lane, sn);
+		r.rev = adapter_scan_right<NW, HASN>(A, T, sh, sl, sn, D2, A.a2h, A.a2l, A.a2n, A.a2mask, A.a2pass, lane);
 	}
 	return r;
 }
@@ -705,20 +736,21 @@ __device__ __noinline__ Step123 steps_special(const KArgs& A, const SmemTables& 
 {
 	Step123 st;
 	st.best_offset = st.fwd = st.rev = -1;
-	uint32_t n1[NW], n2[NW];
+	const int D2 = 32 * NW - P.len2;
+	uint32_t n1[NW], n2r[NW];
 	bool other1, other2;
-	pack_special<NW>(P.r1, P.len1, lane, n1, hasN1, other1);
-	pack_special<NW>(P.r2, P.len2, lane, n2, hasN2, other2);
+	pack_special<NW>(P.r1, P.len1, 0, lane, n1, hasN1, other1);
+	pack_special<NW>(P.r2, P.len2, D2, lane, n2r, hasN2, other2);
 	if (other2)
 	{
 		status = SPG_PAIR_BAD_BASE_R2; // Sequence::complement throws (Sequence.cpp:46-71)
 		return st;
 	}
 	if (other1) return steps_bytewise(A, T, P, lane); // read 1 bytes are compared as plain bytes by the reference
-	Planes<NW> f1, f2;
-	pack_forward<NW>(P.r1, P.len1, lane, f1);
-	pack_forward<NW>(P.r2, P.len2, lane, f2);
-	return steps_planes<NW, true>(A, T, P, f1, f2, n1, n2, lane);
+	Planes<NW> f1, f2r;
+	pack_forward<NW>(P.r1, P.len1, 0, lane, f1);
+	pack_forward<NW>(P.r2, P.len2, D2, lane, f2r);
+	return steps_planes<NW, true>(A, T, P, f1, f2r, D2, n1, n2r, lane);
 }
 
 // pairs that do not fit the plane path (long reads, forced byte-wise mode)
@@ -755,14 +787,15 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 
 	if (NW > 0 && max(P.len1, P.len2) <= 32 * NW && !A.force_bytewise)
 	{
-		Planes<NWP> f1, f2;
-		const bool bad1 = pack_forward<NWP>(P.r1, P.len1, lane, f1);
-		const bool bad2 = pack_forward<NWP>(P.r2, P.len2, lane, f2);
+		Planes<NWP> f1, f2r;
+		const int D2 = 32 * NWP - P.len2; // read 2 is packed right aligned
+		const bool bad1 = pack_forward<NWP>(P.r1, P.len1, 0, lane, f1);
+		const bool bad2 = pack_forward<NWP>(P.r2, P.len2, D2, lane, f2r);
 		if (__any_sync(kFull, bad1 || bad2)) st = steps_special<NWP>(A, T, P, lane, hasN1, hasN2, status); // rare
 		else
 		{
 			uint32_t none[NWP];
-			st = steps_planes<NWP, false>(A, T, P, f1, f2, none, none, lane);
+			st = steps_planes<NWP, false>(A, T, P, f1, f2r, D2, none, none, lane);
 		}
 	}
 	else st = steps_long(A, T, P, lane, hasN1, hasN2, status);
@@ -863,7 +896,13 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 	const uint32_t smem_base = smem_u32(smem);
 
 	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads) T.mmin[i] = A.mmin[i];
-	if (threadIdx.x < 21) T.passA[threadIdx.x] = A.passA[threadIdx.x];
+	if (threadIdx.x < 21)
+	{
+		T.passA[threadIdx.x] = A.passA[threadIdx.x];
+		uint32_t bm = 0; // re-index by mismatches: bit j <- bit (T - j)
+		for (int j = 0; j <= (int)threadIdx.x; ++j) bm |= ((A.passA[threadIdx.x] >> (threadIdx.x - j)) & 1u) << j;
+		T.passM[threadIdx.x] = bm;
+	}
 	if (threadIdx.x == 0)
 	{
 		for (int s = 0; s < A.stages; ++s)
@@ -924,9 +963,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 			const uint32_t lens = st + 4 * plane_bytes;
 			for (;;)
 			{
-				int pr = 0;
+				// lane 0 claims the next pair; the index is broadcast with a warp reduction, whose result lives in a uniform
+				// register, so the compiler knows that the loop exit (and everything below) is warp-uniform
+				int pr = 0x7fffffff;
 				if (lane == 0) pr = atomicAdd(&next_pair[s], 1);
-				pr = __shfl_sync(kFull, pr, 0);
+				pr = __reduce_min_sync(kFull, pr);
 				if (pr >= cnt) break;
 				const uint32_t roff = (uint32_t)pr * (uint32_t)A.stride;
 				Pair P;
