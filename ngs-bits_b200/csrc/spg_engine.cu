@@ -278,7 +278,7 @@ void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 {
 	int tp = (int)(24576 / (4 * (size_t)stride + 4)) / 8 * 8;
 	if (tp < 8) tp = 8;
-	if (tp > 32) tp = 32; // sweeps: 32 pairs per tile is the sweet spot (larger tiles lower occupancy through shared memory)
+	if (tp > 40) tp = 40; // sweeps: 32-40 pairs per tile is the sweet spot (larger tiles lower occupancy through shared memory)
 	tile_pairs = tp;
 	stages = 2;
 	smem = (size_t)stages * (4 * (size_t)tp * stride + 4 * (size_t)tp);

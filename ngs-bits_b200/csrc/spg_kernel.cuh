@@ -639,32 +639,56 @@ __device__ __forceinline__ int step1_planes(const KArgs& A, const SmemTables& T,
 }
 
 // steps 2/3 on forward planes (AnalysisWorker.cpp:307-353, :355-407): first offset at which the adapter matches.
-// sh/sl(/sn): forward planes of the read shifted by lane. Each lane notes its passing rounds; one vote per read.
-template <int NW, bool HASN>
-__device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTables& T, const uint32_t (&sh)[NW], const uint32_t (&sl)[NW], const uint32_t (&sn)[NW],
-                                                   int len, uint32_t ah, uint32_t al, uint32_t an, uint32_t amask, uint32_t pass_by_mm, int lane)
+// sh/sl(/sn): left-aligned forward planes of the read shifted by lane. Each lane notes its passing rounds; one vote per read.
+// QF = number of leading rounds in which every lane has the full adapter window inside the read (32*q+31+a_size <= len): those
+// need no per-lane mask. The caller dispatches on QF once per read, so the rounds themselves are free of branches.
+// amask: the a_size adapter positions that are not N; pass_by_mm: bit j set = a full window with j mismatches passes.
+template <int NW, bool HASN, int QF>
+__device__ __forceinline__ uint32_t adapter_scan_rounds(const KArgs& A, const SmemTables& T, const uint32_t (&sh)[NW], const uint32_t (&sl)[NW], const uint32_t (&sn)[NW],
+                                                        int len, uint32_t ah, uint32_t al, uint32_t an, uint32_t amask, uint32_t pass_by_mm, int lane)
 {
-	// amask: the a_size adapter positions that are not N; pass_by_mm: bit j set = a full window with j mismatches passes
-	// (both host-built, KArgs). Bit q of pm: this lane's offset 32*q+lane passes.
-	uint32_t pm = 0;
+	uint32_t pm = 0; // bit q: this lane's offset 32*q+lane passes
 #pragma unroll
 	for (int q = NW - 1; q >= 0; --q)
 	{
 		uint32_t bit;
-		if (!HASN && 32 * q + 31 + A.a_size <= len) // warp-uniform: every lane has the full adapter window inside the read
-		{
-			bit = pass_by_mm >> __popc(((sh[q] ^ ah) | (sl[q] ^ al)) & amask);
-		}
+		const uint32_t x = (sh[q] ^ ah) | (sl[q] ^ al);
+		if (q < QF && !HASN) bit = pass_by_mm >> __popc(x & amask);
 		else
 		{
 			const int cnt = min(A.a_size, len - 32 * q - lane); // compared bases (the read end cuts the window); <= 0: none
 			uint32_t valid = low_bits(cnt) & ~an;
 			if (HASN) valid &= ~sn[q];
-			const int tot = __popc(valid);
-			bit = cnt > 0 ? T.passA[tot] >> (tot - __popc(((sh[q] ^ ah) | (sl[q] ^ al)) & valid)) : 0u;
+			bit = cnt > 0 ? T.passM[__popc(valid)] >> __popc(x & valid) : 0u;
 		}
 		pm = pm * 2u + (bit & 1u);
 	}
+	return pm;
+}
+
+template <int NW, bool HASN>
+__device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTables& T, const uint32_t (&sh)[NW], const uint32_t (&sl)[NW], const uint32_t (&sn)[NW],
+                                                   int len, uint32_t ah, uint32_t al, uint32_t an, uint32_t amask, uint32_t pass_by_mm, int lane)
+{
+	const int full = HASN ? 0 : (len - 31 - A.a_size >= 0 ? ((len - 31 - A.a_size) >> 5) + 1 : 0); // warp-uniform
+	uint32_t pm;
+	static_assert(NW <= 10, "extend the dispatch");
+#define SPG_SCAN(QF) pm = adapter_scan_rounds<NW, HASN, (QF) <= NW ? (QF) : NW>(A, T, sh, sl, sn, len, ah, al, an, amask, pass_by_mm, lane)
+	switch (full)
+	{
+		case 0: SPG_SCAN(0); break;
+		case 1: SPG_SCAN(1); break;
+		case 2: SPG_SCAN(2); break;
+		case 3: SPG_SCAN(3); break;
+		case 4: SPG_SCAN(4); break;
+		case 5: SPG_SCAN(5); break;
+		case 6: SPG_SCAN(6); break;
+		case 7: SPG_SCAN(7); break;
+		case 8: SPG_SCAN(8); break;
+		case 9: SPG_SCAN(9); break;
+		default: SPG_SCAN(10); break;
+	}
+#undef SPG_SCAN
 	if (!__any_sync(kFull, pm != 0)) return -1; // the common case: one vote per read
 	// lowest passing offset over all lanes
 	const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane) : 0xFFFFFFFFu;
