@@ -154,6 +154,13 @@ __device__ __forceinline__ uint32_t comp_base(uint32_t c) // Sequence::complemen
 {
 	return c == 'A' ? 'T' : c == 'T' ? 'A' : c == 'C' ? 'G' : c == 'G' ? 'C' : 'N';
 }
+// ballot of (v & bits) != 0 over the full warp (and + setp fuse into one LOP3 with predicate output)
+__device__ __forceinline__ uint32_t ballot_bits(uint32_t v, uint32_t bits)
+{
+	uint32_t r;
+	asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}" : "=r"(r) : "r"(v), "r"(bits));
+	return r;
+}
 // low `nb` bits set, for any int nb (<=0 -> 0, >=32 -> all)
 __device__ __forceinline__ uint32_t low_bits(int nb) { return __funnelshift_rc(kFull, 0u, (uint32_t)max(32 - nb, 0)); }
 
@@ -317,6 +324,50 @@ __device__ __forceinline__ int trim_quality_warp(const KArgs& A, uint32_t q, int
 	const uint32_t x = ~low << (31 - t);                              // bit 31 = "base at lane t is not low", then downwards
 	if (x == 0) return trim_quality_general(A, q, count, lane);       // low bases all the way to the start of this block: rare
 	return base + t + 1 - __clz(x);
+}
+
+// Both reads of a pair in one pass: lanes 0-15 hold the last 16 qualities of read 1, lanes 16-31 those of read 2 (segmented
+// warp scan of width 16). Covers trimming points within the last 17-window bases of each read; a read that needs more (or a
+// window > 8, or a read shorter than the window) takes trim_quality_warp / trim_quality_general.
+__device__ __forceinline__ void trim_quality_pair(const KArgs& A, const Pair& P, int n1, int n2, int lane, int& t1, int& t2)
+{
+	const int window = A.qwin;
+	if (window > 8 || n1 < window || n2 < window)
+	{
+		t1 = trim_quality_warp(A, P.q1, n1, lane);
+		t2 = trim_quality_warp(A, P.q2, n2, lane);
+		return;
+	}
+	const bool second = lane >= 16;
+	const int hl = lane & 15;
+	const int base = (second ? n2 : n1) - 16;
+	const int i = base + hl;
+	int v = 0;
+	if (i >= 0) v = qual_at(second ? P.q2 : P.q1, i, A.qoff);
+	int p = v;
+#pragma unroll
+	for (int d = 1; d < 16; d <<= 1) // inclusive scan inside each half warp (c = (32-16)<<8: segment width 16)
+		asm volatile("{\n\t.reg .pred g;\n\t.reg .s32 t;\n\tshfl.sync.up.b32 t|g, %0, %1, 0x1000, 0xffffffff;\n\t@g add.s32 %0, %0, t;\n\t}" : "+r"(p) : "r"(d));
+	const int s = __shfl_sync(kFull, p, hl + window - 1, 16) - p + v; // window sum for hl <= 16-window
+	const uint32_t okm = __ballot_sync(kFull, i >= 0 && hl <= 16 - window && s >= A.qthr);
+	const uint32_t low = __ballot_sync(kFull, i >= 0 && v < A.qcut);
+#pragma unroll
+	for (int r = 0; r < 2; ++r)
+	{
+		const uint32_t ok_r = (okm >> (16 * r)) & 0xFFFFu;
+		const uint32_t low_r = low >> (16 * r);
+		const int n_r = r ? n2 : n1;
+		int res = -1;
+		if (ok_r)
+		{
+			const int t = 31 - __clz(ok_r) + window - 1; // index (0..15) of the last base of the highest passing window
+			const uint32_t x = ~low_r << (31 - t);       // bit 31 = "base t is not low", then downwards; bits above t fall out
+			if (x) res = n_r - 16 + t + 1 - __clz(x);
+		}
+		if (res < 0) res = trim_quality_general(A, r ? P.q2 : P.q1, n_r, lane); // rare: trimming point further left
+		if (r) t2 = res;
+		else t1 = res;
+	}
 }
 
 // ---- FastqEntry::trimN (src/cppNGS/FastqFileStream.cpp:89-117), warp-parallel over run starts; only reads that hold an N get here ----------
@@ -517,8 +568,8 @@ __device__ __forceinline__ bool pack_forward(uint32_t row, int len, int D, int l
 		uint32_t c = 'A';
 		const int pos = 32 * w + lane - D;
 		if ((unsigned)pos < (unsigned)len) c = lds_u8(row + pos);
-		pl.h[w] = __ballot_sync(kFull, c & 4u);
-		pl.l[w] = __ballot_sync(kFull, c & 2u);
+		pl.h[w] = ballot_bits(c, 4u);
+		pl.l[w] = ballot_bits(c, 2u);
 		// a byte is A/C/G/T iff it equals the letter its own 2-bit code stands for
 		bad |= ((__byte_perm(0x47544341u, 0u, (c >> 1) & 3u) ^ c) & 0xFFu) != 0u;
 	}
@@ -856,8 +907,8 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 	{
 		if (A.qcut > 0) // :430-434
 		{
-			const int t1 = trim_quality_warp(A, P.q1, n1, lane);
-			const int t2 = trim_quality_warp(A, P.q2, n2, lane);
+			int t1, t2;
+			trim_quality_pair(A, P, n1, n2, lane, t1, t2);
 			if (t1 < n1) flags |= SPG_F_Q1;
 			if (t2 < n2) flags |= SPG_F_Q2;
 			n1 = t1;
