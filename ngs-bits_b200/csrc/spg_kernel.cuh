@@ -452,6 +452,13 @@ struct Step123
 	int best_offset; // insert-match offset, -1 none
 	int fwd, rev;    // adapter-only offsets, -1 none
 };
+// result of the out-of-line paths (returned by value so that the common path keeps everything in registers)
+struct RareSteps
+{
+	Step123 st;
+	int status; // SPG_PAIR_*
+	int hasN;   // bit 0: read 1 holds an N, bit 1: read 2
+};
 
 // ---- byte-wise path: steps 1-3 straight from the staged ASCII rows (any byte values, any length < 1000) ------------------------------------
 __device__ __forceinline__ uint32_t candidate_key_lane(const KArgs& A, const Pair& P, int o, int m, int mm)
@@ -555,13 +562,13 @@ struct Planes
 	uint32_t h[NW], l[NW];
 };
 
-// forward planes of one read; returns (per lane) whether one of its bytes is not A/C/G/T.
+// forward planes of one read; returns (per lane, in the low byte) whether one of its bytes is not A/C/G/T.
 // D = 0: left aligned (bit b of word w is position 32*w+b). D = 32*NW-len: right aligned (position p sits at bit p+D, the read
 // ends at the top of the last word) -- used for read 2, see planes_revcomp_shifted and adapter_scan_right.
 template <int NW>
-__device__ __forceinline__ bool pack_forward(uint32_t row, int len, int D, int lane, Planes<NW>& pl)
+__device__ __forceinline__ uint32_t pack_forward(uint32_t row, int len, int D, int lane, Planes<NW>& pl)
 {
-	bool bad = false;
+	uint32_t bad = 0; // low byte != 0: one of this lane's bytes is not A/C/G/T
 #pragma unroll
 	for (int w = 0; w < NW; ++w)
 	{
@@ -571,7 +578,7 @@ __device__ __forceinline__ bool pack_forward(uint32_t row, int len, int D, int l
 		pl.h[w] = ballot_bits(c, 4u);
 		pl.l[w] = ballot_bits(c, 2u);
 		// a byte is A/C/G/T iff it equals the letter its own 2-bit code stands for
-		bad |= ((__byte_perm(0x47544341u, 0u, (c >> 1) & 3u) ^ c) & 0xFFu) != 0u;
+		bad |= __byte_perm(0x47544341u, 0u, (c >> 1) & 3u) ^ c;
 	}
 	return bad;
 }
@@ -671,7 +678,7 @@ __device__ __forceinline__ int step1_planes(const KArgs& A, const SmemTables& T,
 		if (HASN) totq[q] = tot;
 		if (o >= 1 && tot > 0 && tot - mm >= (int)T.mmin[tot]) smask |= 1u << q;
 	}
-	if (!__any_sync(kFull, smask != 0)) return -1; // the common case for pairs without an insert match
+	if (ballot_bits(smask, kFull) == 0) return -1; // the common case for pairs without an insert match
 	uint32_t key = kNoKey; // warp-uniform
 #pragma unroll
 	for (int q = 0; q < NW; ++q)
@@ -740,7 +747,7 @@ __device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTab
 		default: SPG_SCAN(10); break;
 	}
 #undef SPG_SCAN
-	if (!__any_sync(kFull, pm != 0)) return -1; // the common case: one vote per read
+	if (ballot_bits(pm, kFull) == 0) return -1; // the common case: one vote per read
 	// lowest passing offset over all lanes
 	const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane) : 0xFFFFFFFFu;
 	return (int)__reduce_min_sync(kFull, mine);
@@ -770,7 +777,7 @@ __device__ __forceinline__ int adapter_scan_right(const KArgs& A, const SmemTabl
 	}
 	// bits k < D are padding in front of the read: drop the rounds that start there (32*q + lane < D)
 	pm &= ~low_bits((D - lane + 31) >> 5);
-	if (!__any_sync(kFull, pm != 0)) return -1;
+	if (ballot_bits(pm, kFull) == 0) return -1;
 	const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane - D) : 0xFFFFFFFFu;
 	return (int)__reduce_min_sync(kFull, mine);
 }
@@ -807,32 +814,35 @@ __device__ __forceinline__ Step123 steps_planes(const KArgs& A, const SmemTables
 // pairs in which a byte other than A/C/G/T was seen: N planes, or the byte-wise path for anything else.
 // status: SPG_PAIR_OK or SPG_PAIR_BAD_BASE_R2.
 template <int NW>
-__device__ __noinline__ Step123 steps_special(const KArgs& A, const SmemTables& T, Pair P, int lane, bool& hasN1, bool& hasN2, int& status)
+__device__ __noinline__ RareSteps steps_special(const KArgs& A, const SmemTables& T, Pair P, int lane)
 {
-	Step123 st;
-	st.best_offset = st.fwd = st.rev = -1;
+	RareSteps r;
+	r.st.best_offset = r.st.fwd = r.st.rev = -1;
+	r.status = SPG_PAIR_OK;
 	const int D2 = 32 * NW - P.len2;
 	uint32_t n1[NW], n2r[NW];
-	bool other1, other2;
+	bool hasN1, hasN2, other1, other2;
 	pack_special<NW>(P.r1, P.len1, 0, lane, n1, hasN1, other1);
 	pack_special<NW>(P.r2, P.len2, D2, lane, n2r, hasN2, other2);
-	if (other2)
+	r.hasN = (hasN1 ? 1 : 0) | (hasN2 ? 2 : 0);
+	if (other2) r.status = SPG_PAIR_BAD_BASE_R2; // Sequence::complement throws (Sequence.cpp:46-71)
+	else if (other1) r.st = steps_bytewise(A, T, P, lane); // read 1 bytes are compared as plain bytes by the reference
+	else
 	{
-		status = SPG_PAIR_BAD_BASE_R2; // Sequence::complement throws (Sequence.cpp:46-71)
-		return st;
+		Planes<NW> f1, f2r;
+		pack_forward<NW>(P.r1, P.len1, 0, lane, f1);
+		pack_forward<NW>(P.r2, P.len2, D2, lane, f2r);
+		r.st = steps_planes<NW, true>(A, T, P, f1, f2r, D2, n1, n2r, lane);
 	}
-	if (other1) return steps_bytewise(A, T, P, lane); // read 1 bytes are compared as plain bytes by the reference
-	Planes<NW> f1, f2r;
-	pack_forward<NW>(P.r1, P.len1, 0, lane, f1);
-	pack_forward<NW>(P.r2, P.len2, D2, lane, f2r);
-	return steps_planes<NW, true>(A, T, P, f1, f2r, D2, n1, n2r, lane);
+	return r;
 }
 
 // pairs that do not fit the plane path (long reads, forced byte-wise mode)
-__device__ __noinline__ Step123 steps_long(const KArgs& A, const SmemTables& T, Pair P, int lane, bool& hasN1, bool& hasN2, int& status)
+__device__ __noinline__ RareSteps steps_long(const KArgs& A, const SmemTables& T, Pair P, int lane)
 {
-	Step123 st;
-	st.best_offset = st.fwd = st.rev = -1;
+	RareSteps r;
+	r.st.best_offset = r.st.fwd = r.st.rev = -1;
+	r.status = SPG_PAIR_OK;
 	bool bad2 = false, n1 = false, n2 = false;
 	for (int i = lane; i < P.len2 && i < A.stride; i += 32)
 	{
@@ -842,13 +852,12 @@ __device__ __noinline__ Step123 steps_long(const KArgs& A, const SmemTables& T, 
 	}
 	for (int i = lane; i < P.len1 && i < A.stride; i += 32) n1 |= (lds_u8(P.r1 + i) == 'N');
 	bad2 = __any_sync(kFull, bad2);
-	hasN1 = __any_sync(kFull, n1);
-	hasN2 = __any_sync(kFull, n2);
+	r.hasN = (__any_sync(kFull, n1) ? 1 : 0) | (__any_sync(kFull, n2) ? 2 : 0);
 	const int maxlen = max(P.len1, P.len2);
-	if (bad2) status = SPG_PAIR_BAD_BASE_R2;
-	else if (maxlen >= SPG_MAXLEN || maxlen > A.stride) status = SPG_PAIR_TOO_LONG; // AnalysisWorker.cpp:131-134
-	else st = steps_bytewise(A, T, P, lane);
-	return st;
+	if (bad2) r.status = SPG_PAIR_BAD_BASE_R2;
+	else if (maxlen >= SPG_MAXLEN || maxlen > A.stride) r.status = SPG_PAIR_TOO_LONG; // AnalysisWorker.cpp:131-134
+	else r.st = steps_bytewise(A, T, P, lane);
+	return r;
 }
 
 // ---- one read pair, one warp ------------------------------------------------------------------------------------------------------------
@@ -859,21 +868,27 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 	int status = SPG_PAIR_OK;
 	bool hasN1 = false, hasN2 = false;
 	Step123 st;
-
+	bool rare = true;
 	if (NW > 0 && max(P.len1, P.len2) <= 32 * NW && !A.force_bytewise)
 	{
 		Planes<NWP> f1, f2r;
 		const int D2 = 32 * NWP - P.len2; // read 2 is packed right aligned
-		const bool bad1 = pack_forward<NWP>(P.r1, P.len1, 0, lane, f1);
-		const bool bad2 = pack_forward<NWP>(P.r2, P.len2, D2, lane, f2r);
-		if (__any_sync(kFull, bad1 || bad2)) st = steps_special<NWP>(A, T, P, lane, hasN1, hasN2, status); // rare
-		else
+		const uint32_t bad = pack_forward<NWP>(P.r1, P.len1, 0, lane, f1) | pack_forward<NWP>(P.r2, P.len2, D2, lane, f2r);
+		if (ballot_bits(bad, 0xFFu) == 0) // the common case: only A/C/G/T in both reads
 		{
 			uint32_t none[NWP];
 			st = steps_planes<NWP, false>(A, T, P, f1, f2r, D2, none, none, lane);
+			rare = false;
 		}
 	}
-	else st = steps_long(A, T, P, lane, hasN1, hasN2, status);
+	if (rare)
+	{
+		const RareSteps r = (NW > 0 && max(P.len1, P.len2) <= 32 * NW && !A.force_bytewise) ? steps_special<NWP>(A, T, P, lane) : steps_long(A, T, P, lane);
+		st = r.st;
+		status = r.status;
+		hasN1 = r.hasN & 1;
+		hasN2 = r.hasN & 2;
+	}
 
 	int n1 = P.len1, n2 = P.len2;
 	uint32_t flags = 0;
