@@ -142,6 +142,7 @@ struct SmemTables
 	uint16_t mmin[SPG_MAXLEN];
 	uint32_t passA[21];
 	uint32_t passM[21]; // the same by mismatches: [T] bit j: j mismatches out of T compared bases pass
+	uint8_t not_acgt[256]; // 1 for every byte value except 'A','C','G','T' (validity of a base by one shared-memory load)
 };
 
 __device__ __forceinline__ bool is_acgtn(uint32_t c)
@@ -566,9 +567,10 @@ struct Planes
 // D = 0: left aligned (bit b of word w is position 32*w+b). D = 32*NW-len: right aligned (position p sits at bit p+D, the read
 // ends at the top of the last word) -- used for read 2, see planes_revcomp_shifted and adapter_scan_right.
 template <int NW>
-__device__ __forceinline__ uint32_t pack_forward(uint32_t row, int len, int D, int lane, Planes<NW>& pl)
+__device__ __forceinline__ uint32_t pack_forward(const SmemTables& T, uint32_t row, int len, int D, int lane, Planes<NW>& pl)
 {
-	uint32_t bad = 0; // low byte != 0: one of this lane's bytes is not A/C/G/T
+	uint32_t bad = 0; // != 0: one of this lane's bytes is not A/C/G/T
+	const uint32_t lut = smem_u32(T.not_acgt);
 #pragma unroll
 	for (int w = 0; w < NW; ++w)
 	{
@@ -577,8 +579,7 @@ __device__ __forceinline__ uint32_t pack_forward(uint32_t row, int len, int D, i
 		if ((unsigned)pos < (unsigned)len) c = lds_u8(row + pos);
 		pl.h[w] = ballot_bits(c, 4u);
 		pl.l[w] = ballot_bits(c, 2u);
-		// a byte is A/C/G/T iff it equals the letter its own 2-bit code stands for
-		bad |= __byte_perm(0x47544341u, 0u, (c >> 1) & 3u) ^ c;
+		bad |= lds_u8(lut + c); // table lookup instead of arithmetic: keeps the ALU pipe for the sweep
 	}
 	return bad;
 }
@@ -651,9 +652,10 @@ __device__ __forceinline__ int step1_planes(const KArgs& A, const SmemTables& T,
                                             const uint32_t (&n1)[NW], const uint32_t (&n2s)[NW], int lane)
 {
 	const int L = min(P.len1, P.len2);
+	// mw[w] = low_bits(L - 32*w - lane), formed as the warp-uniform "position < L" bit string funnel-shifted by lane
 	uint32_t mw[NW];
 #pragma unroll
-	for (int w = 0; w < NW; ++w) mw[w] = low_bits(L - 32 * w - lane);
+	for (int w = 0; w < NW; ++w) mw[w] = __funnelshift_r(low_bits(L - 32 * w), (w + 1 < NW) ? low_bits(L - 32 * (w + 1)) : 0u, lane);
 	// survivors of the pre-filter are rare: every lane notes its own (bit q of smask) and the warp votes once after the sweep
 	uint32_t smask = 0;
 	int mmq[NW], totq[NW];
@@ -830,8 +832,8 @@ __device__ __noinline__ RareSteps steps_special(const KArgs& A, const SmemTables
 	else
 	{
 		Planes<NW> f1, f2r;
-		pack_forward<NW>(P.r1, P.len1, 0, lane, f1);
-		pack_forward<NW>(P.r2, P.len2, D2, lane, f2r);
+		pack_forward<NW>(T, P.r1, P.len1, 0, lane, f1);
+		pack_forward<NW>(T, P.r2, P.len2, D2, lane, f2r);
 		r.st = steps_planes<NW, true>(A, T, P, f1, f2r, D2, n1, n2r, lane);
 	}
 	return r;
@@ -873,8 +875,8 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 	{
 		Planes<NWP> f1, f2r;
 		const int D2 = 32 * NWP - P.len2; // read 2 is packed right aligned
-		const uint32_t bad = pack_forward<NWP>(P.r1, P.len1, 0, lane, f1) | pack_forward<NWP>(P.r2, P.len2, D2, lane, f2r);
-		if (ballot_bits(bad, 0xFFu) == 0) // the common case: only A/C/G/T in both reads
+		const uint32_t bad = pack_forward<NWP>(T, P.r1, P.len1, 0, lane, f1) | pack_forward<NWP>(T, P.r2, P.len2, D2, lane, f2r);
+		if (ballot_bits(bad, 1u) == 0) // the common case: only A/C/G/T in both reads
 		{
 			uint32_t none[NWP];
 			st = steps_planes<NWP, false>(A, T, P, f1, f2r, D2, none, none, lane);
@@ -986,6 +988,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 	const uint32_t smem_base = smem_u32(smem);
 
 	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads) T.mmin[i] = A.mmin[i];
+	for (int i = threadIdx.x; i < 256; i += kThreads) T.not_acgt[i] = (i == 'A' || i == 'C' || i == 'G' || i == 'T') ? 0 : 1;
 	if (threadIdx.x < 21)
 	{
 		T.passA[threadIdx.x] = A.passA[threadIdx.x];
