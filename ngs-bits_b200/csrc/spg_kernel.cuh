@@ -7,7 +7,8 @@
 //     (cp.async.bulk + mbarrier, a dedicated producer warp, NS-deep ring); consumer warps claim pairs of the staged tile
 //     from a shared counter,
 //   * packs every read into two bit planes (hi/lo bit of a 2-bit base code) with warp ballots; every lane then holds the
-//     whole read in registers,
+//     whole read in registers. Read 2 is packed right-aligned, so that revcomp(read 2) is just the reversed bit string
+//     (BREV per word) with the hi plane complemented -- no second pass over its bytes,
 //   * evaluates 32 insert offsets per round: lane l owns the offsets o with o mod 32 == l, so the view of revcomp(read 2)
 //     it needs is "planes shifted right by l bits" -- NW funnel shifts per plane, formed once -- and word indices are
 //     compile-time constants,
