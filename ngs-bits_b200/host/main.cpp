@@ -6,6 +6,11 @@
 // Jobs are dealt to the GPUs round robin (slot s -> device s % n) and retired in submission order, so the output equals the
 // reference's `-threads 1` output whatever the number of GPUs. Not supported here: -qc (qcML report), -debug, -progress.
 #include <chrono>
+#include <condition_variable>
+#include <exception>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -70,7 +75,8 @@ struct OutputStreams
 	std::unique_ptr<FastqOutfileStream> ostream1, ostream2, ostream3, ostream4;
 };
 
-// OutputWorker::run + FastqWriter::run (src/SeqPurge/OutputWorker.cpp:19-103, src/SeqPurge/FastqWriter.cpp:17-38)
+// OutputWorker::run + FastqWriter::run for the forward reads (src/SeqPurge/OutputWorker.cpp:19-103, src/SeqPurge/FastqWriter.cpp:17-38);
+// the reverse reads of complete pairs are written by the second writer thread, like the reference's second FastqWriter
 void writeJob(AnalysisJob& job, OutputStreams& streams, const TrimmingParameters& params, TrimmingStatistics& stats)
 {
 	int reads_removed = 0;
@@ -82,7 +88,6 @@ void writeJob(AnalysisJob& job, OutputStreams& streams, const TrimmingParameters
 		if (e1.bases.size() >= min_len && e2.bases.size() >= min_len)
 		{
 			streams.ostream1->write(e1, e1.bases.size());
-			streams.ostream2->write(e2, e2.bases.size());
 		}
 		else if (streams.ostream3 && e1.bases.size() >= min_len)
 		{
@@ -248,36 +253,166 @@ int main(int argc, char** argv)
 			engine_max_len = max_len;
 		};
 
+		// ---- pipeline: reader thread -> this thread (GPU hand-off, in submission order) -> two writer threads ------------------------------
+		// Same stages as the reference (1 reader, analysis, 1 writer with one thread per output stream; ThreadCoordinator.cpp:40-42,
+		// OutputWorker.cpp:24-32), but jobs retire strictly in input order.
+		enum { FREE, LOADED, IN_FLIGHT, ANALYZED };
+		std::mutex mu;
+		std::condition_variable cv;
+		std::vector<int> state((size_t)n_jobs, FREE);
+		std::vector<int> writers_left((size_t)n_jobs, 0);
+		std::deque<int> loaded, to_write1, to_write2;
+		bool reader_done = false, analysis_done = false, abort_all = false;
+		std::exception_ptr failure;
+		auto fail = [&](std::exception_ptr e) {
+			std::lock_guard<std::mutex> g(mu);
+			if (!failure) failure = e;
+			abort_all = true;
+			cv.notify_all();
+		};
+
+		std::thread reader([&]() {
+			try
+			{
+				int j = 0;
+				bool end = false;
+				while (!end)
+				{
+					{
+						std::unique_lock<std::mutex> l(mu);
+						cv.wait(l, [&] { return state[(size_t)j] == FREE || abort_all; });
+						if (abort_all) return;
+					}
+					end = loadJob(job_pool[(size_t)j], in, params);
+					if (job_pool[(size_t)j].read_count > 0)
+					{
+						std::lock_guard<std::mutex> g(mu);
+						state[(size_t)j] = LOADED;
+						loaded.push_back(j);
+						cv.notify_all();
+						j = (j + 1) % n_jobs;
+					}
+				}
+				std::lock_guard<std::mutex> g(mu);
+				reader_done = true;
+				cv.notify_all();
+			}
+			catch (...)
+			{
+				fail(std::current_exception());
+			}
+		});
+
+		auto writer = [&](std::deque<int>& queue, bool first) {
+			try
+			{
+				for (;;)
+				{
+					int j;
+					{
+						std::unique_lock<std::mutex> l(mu);
+						cv.wait(l, [&] { return !queue.empty() || analysis_done || abort_all; });
+						if (abort_all) return;
+						if (queue.empty()) return; // analysis_done
+						j = queue.front();
+						queue.pop_front();
+					}
+					AnalysisJob& job = job_pool[(size_t)j];
+					if (first) writeJob(job, out, params, stats); // out1, singletons, statistics
+					else
+					{
+						const size_t min_len = (size_t)std::max(params.min_len, 0);
+						for (int r = 0; r < job.read_count; ++r) // FastqWriter::run for the reverse reads
+						{
+							const FastqEntry& e1 = job.r1[(size_t)r];
+							const FastqEntry& e2 = job.r2[(size_t)r];
+							if (e1.bases.size() >= min_len && e2.bases.size() >= min_len) out.ostream2->write(e2, e2.bases.size());
+						}
+					}
+					std::lock_guard<std::mutex> g(mu);
+					if (--writers_left[(size_t)j] == 0)
+					{
+						state[(size_t)j] = FREE;
+						cv.notify_all();
+					}
+				}
+			}
+			catch (...)
+			{
+				fail(std::current_exception());
+			}
+		};
+		std::thread writer1(writer, std::ref(to_write1), true);
+		std::thread writer2(writer, std::ref(to_write2), false);
+
 		std::deque<int> in_flight; // job indices in submission order
 		auto retire = [&]() {
 			const int j = in_flight.front();
 			in_flight.pop_front();
 			workers[(size_t)j]->wait();
-			writeJob(job_pool[(size_t)j], out, params, stats);
+			std::lock_guard<std::mutex> g(mu);
+			state[(size_t)j] = ANALYZED;
+			writers_left[(size_t)j] = 2;
+			to_write1.push_back(j);
+			to_write2.push_back(j);
+			cv.notify_all();
 		};
-
-		bool end_of_data = false;
-		int next_job = 0;
-		while (!end_of_data)
+		try
 		{
-			if ((int)in_flight.size() == n_jobs) retire();
-			AnalysisJob& job = job_pool[(size_t)next_job];
-			end_of_data = loadJob(job, in, params);
-			if (job.read_count > 0)
+			for (;;)
 			{
+				int j = -1;
+				{
+					std::unique_lock<std::mutex> l(mu);
+					// start a loaded job if there is one; otherwise retire the oldest job in flight; otherwise wait for the reader
+					cv.wait(l, [&] { return !loaded.empty() || !in_flight.empty() || reader_done || abort_all; });
+					if (abort_all) break;
+					if (!loaded.empty())
+					{
+						j = loaded.front();
+						loaded.pop_front();
+					}
+					else if (in_flight.empty() && reader_done) break;
+				}
+				if (j < 0)
+				{
+					retire();
+					continue;
+				}
+				AnalysisJob& job = job_pool[(size_t)j];
 				const int need = std::min(maxReadLength(job), MAXLEN - 1);
 				if (!engine || need > engine_max_len)
 				{
 					while (!in_flight.empty()) retire(); // drain before the slots are re-created for longer reads
 					createEngine(std::min(MAXLEN - 1, std::max((need + 15) / 16 * 16, 160)));
 				}
-				workers[(size_t)next_job].reset(new GpuAnalysisWorker(job, params, stats, ec_stats, engine, next_job));
-				workers[(size_t)next_job]->start();
-				in_flight.push_back(next_job);
-				next_job = (next_job + 1) % n_jobs;
+				workers[(size_t)j].reset(new GpuAnalysisWorker(job, params, stats, ec_stats, engine, j));
+				workers[(size_t)j]->start();
+				{
+					std::lock_guard<std::mutex> g(mu);
+					state[(size_t)j] = IN_FLIGHT;
+				}
+				in_flight.push_back(j);
 			}
+			while (!in_flight.empty() && !abort_all) retire();
 		}
-		while (!in_flight.empty()) retire();
+		catch (...)
+		{
+			fail(std::current_exception());
+		}
+		{
+			std::lock_guard<std::mutex> g(mu);
+			analysis_done = true;
+			cv.notify_all();
+		}
+		reader.join();
+		writer1.join();
+		writer2.join();
+		if (failure)
+		{
+			if (engine) spg_destroy(engine);
+			std::rethrow_exception(failure);
+		}
 		accumulateEc();
 		if (engine) spg_destroy(engine);
 
