@@ -82,7 +82,7 @@ def test_cli_multiple_input_files_and_small_prefetch(cli, tmp_path):
 
 def test_cli_header_mismatch_is_an_error(cli, tmp_path):
     r = subprocess.run([cli, "-in1", f"{G}/SeqPurge_in1.fastq.gz", "-in2", f"{G}/SeqPurge_in4.fastq.gz", "-out1", str(tmp_path / "a.gz"), "-out2", str(tmp_path / "b.gz"),
-                        "-block_size", "100"], capture_output=True, text=True)
+                        "-block_size", "100", "-block_prefetch", "1"], capture_output=True, text=True)  # one job: the reader cannot run ahead into the length mismatch
     assert r.returncode == 1 and "Headers of reads do not match" in r.stderr
 
 
