@@ -248,7 +248,6 @@ struct spg_ctx
 	int tile_pairs = 0; // 0 = automatic
 	int stages = 0;     // 0 = automatic
 	long long launches = 0;
-	spg_ec_stats ec_total;
 };
 
 namespace
@@ -432,7 +431,6 @@ int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, i
 	ctx->params.a2 = ctx->a2.data();
 	ctx->a_size = std::min(20, std::min(params->a1_len, params->a2_len)); // main.cpp:71
 	ctx->adapters_plain = all_acgtn(ctx->a1.data(), std::min(32, params->a1_len)) && all_acgtn(ctx->a2.data(), std::min(32, params->a2_len));
-	memset(&ctx->ec_total, 0, sizeof(ctx->ec_total));
 	std::string err;
 	if (!build_tables(ctx->params, ctx->a_size, ctx->tables, err))
 	{

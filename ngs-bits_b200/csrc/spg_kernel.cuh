@@ -91,12 +91,6 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a)
 	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
 	return v;
 }
-__device__ __forceinline__ uint4 lds_v4(uint32_t a)
-{
-	uint4 v;
-	asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-	return v;
-}
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }

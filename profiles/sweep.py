@@ -19,10 +19,17 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 150
 stride = (L + 15) // 16 * 16
 dev = torch.device("cuda:0")
-if L == 150:
+workload = os.environ.get("SPG_SWEEP_CONFIG", "C2" if L == 150 else "C3")
+params = sp.TrimmingParameters()
+if workload == "C2":
     cfg = sp.SynthConfig(read_len=L)
-else:
+elif workload == "C3":  # high overlap: every pair has an insert match
     cfg = sp.SynthConfig(read_len=L, insert_mean=150, insert_sd=40, insert_max=L - 1)
+elif workload == "C4":  # 2 % errors, long low-quality tails, N runs
+    cfg = sp.SynthConfig(read_len=L, error_rate=0.02, lowq_tail_mean=20.0, n_run_rate=0.005)
+else:  # C5: NovaSeq-like, binned qualities
+    cfg = sp.SynthConfig(read_len=L, insert_mean=350, insert_sd=100, error_rate=0.002, lowq_tail_mean=2.0, binned_quals=True)
+print("workload", workload, flush=True)
 bufs = []
 for b in range(2):
     t = {k: torch.empty((n, stride), dtype=torch.uint8, device=dev) for k in ("bases1", "quals1", "bases2", "quals2")}
@@ -31,7 +38,7 @@ for b in range(2):
     sp.synth_device(cfg, b * n, n, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
     bufs.append((t, l1, l2))
 res = torch.empty((n, 8), dtype=torch.uint8, device=dev)
-eng = sp.Engine(sp.TrimmingParameters(), devices=(0,))
+eng = sp.Engine(params, devices=(0,))
 grid = list(itertools.product((2, 3, 4), (16, 32), (2, 3), (0,)))
 if len(sys.argv) > 3:
     grid = [tuple(int(x) for x in c.split(",")) for c in sys.argv[3:]]
