@@ -1049,14 +1049,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 			const int cnt = (int)min((long long)TP, A.n_pairs - first);
 			const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 			const uint32_t lens = st + 4 * plane_bytes;
+			// lane 0 claims pairs from the tile's counter; the claim for the NEXT pair is issued before the current pair is processed, so
+			// the latency of the shared-memory atomic and of the broadcast is hidden behind a whole pair of work (every warp over-claims
+			// once per tile, which is harmless: the producer resets the counter after all warps have left the stage)
+			int raw = 0x7fffffff;
+			if (lane == 0) raw = atomicAdd(&next_pair[s], 1);
 			for (;;)
 			{
-				// lane 0 claims the next pair; the index is broadcast with a warp reduction, whose result lives in a uniform
-				// register, so the compiler knows that the loop exit (and everything below) is warp-uniform
-				int pr = 0x7fffffff;
-				if (lane == 0) pr = atomicAdd(&next_pair[s], 1);
-				pr = __reduce_min_sync(kFull, pr);
+				const int pr = __reduce_min_sync(kFull, raw); // broadcast of lane 0's claim
 				if (pr >= cnt) break;
+				if (lane == 0) raw = atomicAdd(&next_pair[s], 1);
 				const uint32_t roff = (uint32_t)pr * (uint32_t)A.stride;
 				Pair P;
 				P.r1 = st + roff;
