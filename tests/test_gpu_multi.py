@@ -60,3 +60,49 @@ def test_cli_two_gpus_reproduces_golden(sp, tmp_path):
     for mine, gold in (("o1", 5), ("o2", 6)):
         with gzip.open(tmp_path / f"{mine}.fastq.gz", "rb") as a, gzip.open(f"{G}/SeqPurge_out{gold}.fastq.gz", "rb") as b:
             assert a.read() == b.read()
+
+
+def test_slots_from_concurrent_threads():
+    """The ABI is used per slot from different host threads (the reference's analysis pool runs jobs concurrently,
+    ThreadCoordinator.cpp:40-42): four threads fill, submit and wait for their own slots in a loop; every result equals the oracle."""
+    import threading
+
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import __graft_entry__ as g
+
+    g.build()
+    import seqpurge_b200 as spm
+
+    batch = H.golden_batch(1, 2)
+    want, _ = H.oracle_trim(batch)
+    n_threads, rounds, chunk = 4, 6, 600
+    devices = (0, 1) if torch.cuda.device_count() >= 2 else (0,)
+    eng = spm.Engine(spm.TrimmingParameters(), devices=devices, n_slots=n_threads, max_pairs=chunk, max_len=batch.stride - 1)
+    errors = []
+
+    def work(tid):
+        try:
+            s = eng.slot(tid)
+            for r in range(rounds):
+                st = ((tid * rounds + r) * 97) % (batch.n - chunk)
+                for name in ("bases1", "quals1", "bases2", "quals2"):
+                    getattr(s, name)[:chunk] = getattr(batch, name)[st : st + chunk]
+                s.len1[:chunk] = batch.len1[st : st + chunk]
+                s.len2[:chunk] = batch.len2[st : st + chunk]
+                eng.submit(tid, chunk)
+                got = eng.wait(tid)
+                if not np.array_equal(got.view(np.uint64), want[st : st + chunk].view(np.uint64)):
+                    errors.append((tid, r))
+        except Exception as ex:  # noqa: BLE001
+            errors.append((tid, repr(ex)))
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    eng.close()
+    assert errors == []
