@@ -340,3 +340,28 @@ def test_full_size_config2_properties(sp):
         del t, l1, l2
     eng.close()
     assert sums_planes == sums_bytes, "plane path and byte-wise path disagree"
+
+
+@pytest.mark.parametrize("L", [31, 32, 33, 159, 160, 161, 255, 256, 257, 319, 320, 321, 400])
+def test_plane_width_boundaries(sp, L):
+    """Read lengths around the word / kernel-variant boundaries (NW = 5, 8, 10 plane words, byte-wise beyond 320), ragged lengths."""
+    n = 600 if L <= 320 else 200
+    batch = H.random_batch(n, L, 700 + L, error_rate=0.02, n_rate=0.003, lowq_tail=6.0, ragged=(L % 2 == 0), stride=(L + 1) // 2 * 2 if L >= 16 else 16)
+    want, _ = H.oracle_trim(batch)
+    got, _, _ = gpu_trim(sp, batch)
+    assert_same(got, want, batch)
+
+
+@pytest.mark.parametrize("params", [
+    dict(qwin=40, qcut=20), dict(qwin=1, qcut=30), dict(qwin=16, qcut=10), dict(qwin=17, qcut=25),
+    dict(match_perc=50.0, mep=1e-3), dict(match_perc=100.0), dict(mep=1e-12), dict(ncut=1), dict(qcut=0, ncut=0), dict(qoff=64, qcut=5),
+], ids=lambda p: ",".join(f"{k}={v}" for k, v in p.items()))
+def test_parameter_corners(sp, params):
+    """Window sizes on both sides of the fast paths (<= 8 paired, <= 32 scan, > 32 general), permissive and strict match filters
+    (many / no survivors of the pre-filter), single-N trimming, everything off."""
+    batch = H.random_batch(1500, 150, 900, error_rate=0.04, n_rate=0.004, lowq_tail=25.0, n_runs=0.05)
+    want, _ = H.oracle_trim(batch, **params)
+    got, _, _ = gpu_trim(sp, batch, **params)
+    assert_same(got, want, batch)
+    got2, _, _ = gpu_trim(sp, batch, force_bytewise=True, **params)
+    assert_same(got2, want, batch)
