@@ -62,6 +62,7 @@ typedef struct spg_params
 	int32_t qoff;        /* -qoff 33 */
 	int32_t ncut;        /* -ncut 7 (0 disables) */
 	int32_t ec;          /* -ec: error-correct insert-hit pairs; edited rows are returned in the slot */
+	int32_t qc;          /* -qc: also accumulate the raw-read statistics of every submitted batch (spg_qc_stats_get) */
 } spg_params;
 
 /* Per-pair output: everything OutputWorker / FastqWriter / TrimmingStatistics need (OutputWorker.cpp:36-77). 8 bytes. */
@@ -96,6 +97,25 @@ typedef struct spg_ec_stats
 	int64_t errors_per_read[SPG_MAXLEN];
 } spg_ec_stats;
 
+/* Raw-read statistics of the untrimmed reads, the accumulators of StatisticsReads::update(FastqEntry, direction)
+   (src/cppNGS/StatisticsReads.cpp:26-81) that a paired-end qcML report needs (StatisticsReads::getResult, :140-330);
+   replaces `stats_.qc.update(...)` in AnalysisWorker::run (src/SeqPurge/AnalysisWorker.cpp:86-95). Qualities are Phred+33
+   like FastqEntry::quality()'s default. */
+typedef struct spg_qc_stats
+{
+	int64_t reads_forward;                /* c_forward_ */
+	int64_t reads_reverse;                /* c_reverse_ */
+	int64_t bases_sequenced;              /* bases_sequenced_ */
+	int64_t read_q20;                     /* c_read_q20_: reads with mean quality >= 20 (reads of length 0 do not count) */
+	int64_t base_q20;                     /* c_base_q20_ */
+	int64_t base_q30;                     /* c_base_q30_ */
+	int64_t errors;                       /* != 0: a base Pileup::inc throws on, or a quality outside 0..99 (the reference throws) */
+	int64_t read_lengths[SPG_MAXLEN];     /* read_lengths_[cycles] */
+	int64_t pileup[SPG_MAXLEN][5];        /* pileups_[cycle]: A, C, G, T, N (lower case counted like Pileup::inc) */
+	int64_t qsum_forward[SPG_MAXLEN];     /* qualities1_[cycle] before the division by the depth */
+	int64_t qsum_reverse[SPG_MAXLEN];     /* qualities2_[cycle] */
+} spg_qc_stats;
+
 typedef struct spg_ctx spg_ctx;
 
 /* Replaces: main.cpp:92 (precalculateFactorials), ThreadCoordinator.cpp:40-48 (analysis pool + job pool allocation).
@@ -124,6 +144,14 @@ int spg_trim_device(spg_ctx* ctx, int device_index, void* bases1, void* quals1, 
 
 /* Accumulated -ec histograms of everything waited for so far (Auxilary.h:224-236). */
 int spg_ec_stats_get(spg_ctx* ctx, spg_ec_stats* out);
+
+/* Raw-read statistics of a device-resident batch (same pointer rules as spg_trim_device), added to the context's accumulators
+   on that device. spg_submit does this by itself for every batch when params.qc is set. */
+int spg_qc_device(spg_ctx* ctx, int device_index, const void* bases1, const void* quals1, const void* bases2, const void* quals2, const uint16_t* len1,
+                  const uint16_t* len2, int stride, int64_t n_pairs, void* cuda_stream);
+
+/* Sum of the -qc accumulators of all devices (synchronises the devices' streams first). */
+int spg_qc_stats_get(spg_ctx* ctx, spg_qc_stats* out);
 
 /* Text of the last error on this context (or of the last failed spg_create when ctx is NULL). */
 const char* spg_last_error(spg_ctx* ctx);

@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "spg_kernel.cuh"
+#include "spg_qc.cuh"
 
 namespace
 {
@@ -205,6 +206,7 @@ struct Device
 	uint16_t* d_rank = nullptr;
 	double* d_psmall = nullptr;
 	unsigned long long* d_ec = nullptr; // 3 * SPG_MAXLEN
+	unsigned long long* d_qc = nullptr; // spg::kQcWords accumulators of the -qc statistics
 	int occ[4][3] = {};                 // resident CTAs per SM for NW = 0,5,8,10 x kernel variant (min blocks 2,3,4)
 };
 
@@ -395,6 +397,36 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	return SPG_OK;
 }
 
+int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, const uint8_t* b2, const uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride,
+              long long n, cudaStream_t stream)
+{
+	if (n <= 0) return SPG_OK;
+	spg::QcArgs a;
+	a.b1 = b1;
+	a.q1 = q1;
+	a.b2 = b2;
+	a.q2 = q2;
+	a.len1 = len1;
+	a.len2 = len2;
+	a.n_pairs = n;
+	a.stride = stride;
+	a.acc = d.d_qc;
+	const long long warps_wanted = std::min<long long>((n + 7) / 8, (long long)d.sm_count * 32); // >= 8 pairs per warp, at most 4 CTAs of 8 warps per SM
+	const int blocks = (int)((warps_wanted + 7) / 8);
+	switch (nw_for_stride(stride))
+	{
+		case 5: spg::qc_kernel<5><<<blocks, 256, 0, stream>>>(a); break;
+		case 8: spg::qc_kernel<8><<<blocks, 256, 0, stream>>>(a); break;
+		case 10: spg::qc_kernel<10><<<blocks, 256, 0, stream>>>(a); break;
+		default: spg::qc_kernel_generic<<<blocks, 256, 0, stream>>>(a); break;
+	}
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return fail(ctx, SPG_ERR_CUDA, std::string("qc_kernel launch: ") + cudaGetErrorString(e));
+	std::lock_guard<std::mutex> g(ctx->mu);
+	++ctx->launches;
+	return SPG_OK;
+}
+
 } // namespace
 
 extern "C"
@@ -480,6 +512,8 @@ int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, i
 		CREATE_CUDA(cudaMemcpy(d.d_rank, ctx->tables.ranktab.data(), ctx->tables.ranktab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
 		CREATE_CUDA(cudaMemcpy(d.d_psmall, ctx->tables.psmall.data(), ctx->tables.psmall.size() * sizeof(double), cudaMemcpyHostToDevice));
 		CREATE_CUDA(cudaMemset(d.d_ec, 0, 3 * SPG_MAXLEN * sizeof(unsigned long long)));
+		CREATE_CUDA(cudaMalloc(&d.d_qc, spg::kQcWords * sizeof(unsigned long long)));
+		CREATE_CUDA(cudaMemset(d.d_qc, 0, spg::kQcWords * sizeof(unsigned long long)));
 	}
 	ctx->slots.resize((size_t)n_slots);
 	for (int s = 0; s < n_slots; ++s)
@@ -540,6 +574,12 @@ int spg_submit(spg_ctx* ctx, int slot, int n_pairs)
 			for (int k = 0; k < 4; ++k) SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + k * pb, sl.h_block + k * pb, rows, cudaMemcpyHostToDevice, sl.stream));
 			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb, sl.h_block + 4 * pb, lens, cudaMemcpyHostToDevice, sl.stream));
 			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb + ctx->len_bytes, sl.h_block + 4 * pb + ctx->len_bytes, lens, cudaMemcpyHostToDevice, sl.stream));
+		}
+		if (ctx->params.qc) // raw-read statistics of the untrimmed batch, in front of the trimming kernel on the same stream
+		{
+			int qrc = launch_qc(ctx, d, sl.d_block, sl.d_block + pb, sl.d_block + 2 * pb, sl.d_block + 3 * pb, reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb),
+			                    reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.stream);
+			if (qrc != SPG_OK) return qrc;
 		}
 		int rc = launch_trim(ctx, d, sl.d_block, sl.d_block + pb, sl.d_block + 2 * pb, sl.d_block + 3 * pb, reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb),
 		                     reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.d_res, sl.stream);
@@ -602,6 +642,47 @@ int spg_ec_stats_get(spg_ctx* ctx, spg_ec_stats* out)
 	return SPG_OK;
 }
 
+int spg_qc_device(spg_ctx* ctx, int device_index, const void* bases1, const void* quals1, const void* bases2, const void* quals2, const uint16_t* len1,
+                  const uint16_t* len2, int stride, int64_t n_pairs, void* cuda_stream)
+{
+	if (!ctx) return SPG_ERR_PARAM;
+	if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SPG_ERR_PARAM, "device index out of range");
+	if (stride < 16 || stride % 2 != 0 || stride > 1008) return fail(ctx, SPG_ERR_PARAM, "stride must be even and in [16,1008]");
+	if (n_pairs < 0) return fail(ctx, SPG_ERR_PARAM, "negative n_pairs");
+	Device& d = ctx->devs[(size_t)device_index];
+	SPG_CUDA(ctx, cudaSetDevice(d.id));
+	return launch_qc(ctx, d, (const uint8_t*)bases1, (const uint8_t*)quals1, (const uint8_t*)bases2, (const uint8_t*)quals2, len1, len2, stride, (long long)n_pairs,
+	                 (cudaStream_t)cuda_stream);
+}
+
+int spg_qc_stats_get(spg_ctx* ctx, spg_qc_stats* out)
+{
+	if (!ctx || !out) return SPG_ERR_PARAM;
+	memset(out, 0, sizeof(*out));
+	std::vector<unsigned long long> tmp((size_t)spg::kQcWords);
+	for (Device& d : ctx->devs)
+	{
+		SPG_CUDA(ctx, cudaSetDevice(d.id));
+		SPG_CUDA(ctx, cudaDeviceSynchronize());
+		SPG_CUDA(ctx, cudaMemcpy(tmp.data(), d.d_qc, tmp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+		out->reads_forward += (int64_t)tmp[spg::kQcReadsF];
+		out->reads_reverse += (int64_t)tmp[spg::kQcReadsR];
+		out->bases_sequenced += (int64_t)tmp[spg::kQcBases];
+		out->read_q20 += (int64_t)tmp[spg::kQcReadQ20];
+		out->base_q20 += (int64_t)tmp[spg::kQcBaseQ20];
+		out->base_q30 += (int64_t)tmp[spg::kQcBaseQ30];
+		out->errors += (int64_t)tmp[spg::kQcErrors];
+		for (int i = 0; i < SPG_MAXLEN; ++i)
+		{
+			out->read_lengths[i] += (int64_t)tmp[(size_t)spg::kQcLen + i];
+			for (int k = 0; k < 5; ++k) out->pileup[i][k] += (int64_t)tmp[(size_t)spg::kQcPile + 5 * i + k];
+			out->qsum_forward[i] += (int64_t)tmp[(size_t)spg::kQcQf + i];
+			out->qsum_reverse[i] += (int64_t)tmp[(size_t)spg::kQcQr + i];
+		}
+	}
+	return SPG_OK;
+}
+
 const char* spg_last_error(spg_ctx* ctx)
 {
 	if (!ctx) return g_create_error.c_str();
@@ -639,6 +720,7 @@ void spg_destroy(spg_ctx* ctx)
 		cudaFree(d.d_rank);
 		cudaFree(d.d_psmall);
 		cudaFree(d.d_ec);
+		cudaFree(d.d_qc);
 	}
 	delete ctx;
 }

@@ -21,6 +21,7 @@ spg_params toEngineParams(const TrimmingParameters& p)
 	e.qoff = p.qoff;
 	e.ncut = p.ncut;
 	e.ec = p.ec ? 1 : 0;
+	e.qc = p.qc.empty() ? 0 : 1;
 	return e;
 }
 

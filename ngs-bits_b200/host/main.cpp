@@ -4,7 +4,7 @@
 // handed to the CUDA engine through GpuAnalysisWorker instead of AnalysisWorker + QThreadPool.
 //
 // Jobs are dealt to the GPUs round robin (slot s -> device s % n) and retired in submission order, so the output equals the
-// reference's `-threads 1` output whatever the number of GPUs. Not supported here: -qc (qcML report), -debug, -progress.
+// reference's `-threads 1` output whatever the number of GPUs. -qc writes the read statistics as qcML (values only, no plots). Not supported here: -debug, -progress.
 #include <chrono>
 #include <condition_variable>
 #include <exception>
@@ -22,6 +22,7 @@
 
 #include "FastqFileStream.h"
 #include "GpuAnalysisWorker.h"
+#include "QcReport.h"
 
 using namespace seqpurge;
 
@@ -140,7 +141,7 @@ void usage()
 	std::cout << "seqpurge_b200: removes adapter sequences from paired-end sequencing data (SeqPurge on B200 GPUs).\n"
 	             "Mandatory: -in1 <files> -in2 <files> -out1 <file> -out2 <file>\n"
 	             "Optional (defaults of SeqPurge): -a1 -a2 -match_perc 80 -mep 0.000001 -qcut 15 -qwin 5 -qoff 33 -ncut 7 -min_len 30 -threads 1\n"
-	             "          -out3 <prefix> -summary <file> -block_size 10000 -block_prefetch 32 -ec -compression_level 1\n"
+	             "          -out3 <prefix> -summary <file> -qc <file.qcML> -block_size 10000 -block_prefetch 32 -ec -compression_level 1\n"
 	             "New: -gpus 0[,1,...]  CUDA devices the blocks are dealt to (default 0)\n";
 }
 
@@ -188,7 +189,8 @@ int main(int argc, char** argv)
 			else if (f == "-compression_level") params.compression_level = atoi(next().c_str());
 			else if (f == "-ec") params.ec = true;
 			else if (f == "-gpus") params.gpus = parseIntList(next());
-			else if (f == "-qc" || f == "-debug") throw CommandLineParsingException("Parameter '" + f + "' is not supported by seqpurge_b200.");
+			else if (f == "-qc") params.qc = next();
+			else if (f == "-debug") throw CommandLineParsingException("Parameter '" + f + "' is not supported by seqpurge_b200.");
 			else throw CommandLineParsingException("Unknown parameter '" + f + "'!");
 		}
 		if (params.files_in1.empty() || params.files_in2.empty() || params.out1.empty() || params.out2.empty())
@@ -230,8 +232,17 @@ int main(int argc, char** argv)
 		spg_ctx* engine = nullptr;
 		int engine_max_len = 0;
 		spg_params ep = toEngineParams(params);
-		auto accumulateEc = [&]() {
-			if (!engine || !params.ec) return;
+		std::unique_ptr<spg_qc_stats> qc_stats(new spg_qc_stats());
+		memset(qc_stats.get(), 0, sizeof(spg_qc_stats));
+		auto accumulateEc = [&]() { // takes the -ec histograms and the -qc statistics out of an engine before it goes away
+			if (!engine) return;
+			if (!params.qc.empty())
+			{
+				std::unique_ptr<spg_qc_stats> q(new spg_qc_stats());
+				if (spg_qc_stats_get(engine, q.get()) != SPG_OK) throw Exception(spg_last_error(engine));
+				qcAccumulate(*qc_stats, *q);
+			}
+			if (!params.ec) return;
 			spg_ec_stats s;
 			if (spg_ec_stats_get(engine, &s) != SPG_OK) throw Exception(spg_last_error(engine));
 			for (int i = 0; i < MAXLEN; ++i)
@@ -422,6 +433,12 @@ int main(int argc, char** argv)
 		if (out.ostream4) out.ostream4->close();
 
 		stats.writeStatistics(summary, params);
+		if (!params.qc.empty()) // ThreadCoordinator.cpp:137-141
+		{
+			std::vector<std::string> sources = params.files_in1;
+			sources.insert(sources.end(), params.files_in2.begin(), params.files_in2.end());
+			storeQcML(params.qc, *qc_stats, sources, ""); // the reference passes an empty parameter string, too
+		}
 		if (params.ec) ec_stats.writeStatistics(summary);
 		const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
 		char buf[64];

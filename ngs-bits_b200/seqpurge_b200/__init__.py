@@ -44,8 +44,27 @@ class _Params(C.Structure):
     _fields_ = [
         ("a1", C.c_char_p), ("a1_len", C.c_int32), ("a2", C.c_char_p), ("a2_len", C.c_int32),
         ("adapter_overlap", C.c_int32), ("match_perc", C.c_double), ("mep", C.c_double),
-        ("qcut", C.c_int32), ("qwin", C.c_int32), ("qoff", C.c_int32), ("ncut", C.c_int32), ("ec", C.c_int32),
+        ("qcut", C.c_int32), ("qwin", C.c_int32), ("qoff", C.c_int32), ("ncut", C.c_int32), ("ec", C.c_int32), ("qc", C.c_int32),
     ]
+
+
+class _QcStats(C.Structure):
+    _fields_ = [
+        ("reads_forward", C.c_int64), ("reads_reverse", C.c_int64), ("bases_sequenced", C.c_int64), ("read_q20", C.c_int64),
+        ("base_q20", C.c_int64), ("base_q30", C.c_int64), ("errors", C.c_int64),
+        ("read_lengths", C.c_int64 * MAXLEN), ("pileup", (C.c_int64 * 5) * MAXLEN),
+        ("qsum_forward", C.c_int64 * MAXLEN), ("qsum_reverse", C.c_int64 * MAXLEN),
+    ]
+
+
+def qc_stats_to_dict(st):
+    """ctypes spg_qc_stats / spo_qc_stats -> plain python (ints and numpy arrays)."""
+    d = {k: int(getattr(st, k)) for k in ("reads_forward", "reads_reverse", "bases_sequenced", "read_q20", "base_q20", "base_q30", "errors")}
+    d["read_lengths"] = np.array(st.read_lengths, dtype=np.int64)
+    d["pileup"] = np.array([list(row) for row in st.pileup], dtype=np.int64)
+    d["qsum_forward"] = np.array(st.qsum_forward, dtype=np.int64)
+    d["qsum_reverse"] = np.array(st.qsum_reverse, dtype=np.int64)
+    return d
 
 
 class _SlotView(C.Structure):
@@ -79,6 +98,10 @@ _lib.spg_trim_device.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_
 _lib.spg_trim_device.restype = C.c_int
 _lib.spg_ec_stats_get.argtypes = [C.c_void_p, C.POINTER(_EcStats)]
 _lib.spg_ec_stats_get.restype = C.c_int
+_lib.spg_qc_device.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_int, C.c_int64, C.c_void_p]
+_lib.spg_qc_device.restype = C.c_int
+_lib.spg_qc_stats_get.argtypes = [C.c_void_p, C.POINTER(_QcStats)]
+_lib.spg_qc_stats_get.restype = C.c_int
 _lib.spg_last_error.argtypes = [C.c_void_p]
 _lib.spg_last_error.restype = C.c_char_p
 _lib.spg_destroy.argtypes = [C.c_void_p]
@@ -106,10 +129,11 @@ class TrimmingParameters:
     qoff: int = 33
     ncut: int = 7
     ec: bool = False
+    qc: bool = False
 
     def _c(self):
         a1, a2 = self.a1.encode(), self.a2.encode()
-        p = _Params(a1, len(a1), a2, len(a2), self.adapter_overlap, self.match_perc, self.mep, self.qcut, self.qwin, self.qoff, self.ncut, int(self.ec))
+        p = _Params(a1, len(a1), a2, len(a2), self.adapter_overlap, self.match_perc, self.mep, self.qcut, self.qwin, self.qoff, self.ncut, int(self.ec), int(self.qc))
         p._keep = (a1, a2)
         return p
 
@@ -211,6 +235,23 @@ class Engine:
         st = _EcStats()
         self._check(_lib.spg_ec_stats_get(self._h, C.byref(st)), "spg_ec_stats_get")
         return {k: np.array(getattr(st, k), dtype=np.int64) for k in ("mismatch_r1", "mismatch_r2", "errors_per_read")}
+
+    def qc_device(self, bases1, quals1, bases2, quals2, len1, len2, n_pairs=None, device_index=0, stream=None):
+        """Raw-read statistics (-qc) of a device-resident batch (torch CUDA tensors as in trim_device), added to the context's accumulators."""
+        import torch
+
+        n = bases1.shape[0] if n_pairs is None else n_pairs
+        if stream is None:
+            stream = torch.cuda.current_stream(bases1.device).cuda_stream
+        rc = _lib.spg_qc_device(self._h, device_index, bases1.data_ptr(), quals1.data_ptr(), bases2.data_ptr(), quals2.data_ptr(), len1.data_ptr(),
+                                len2.data_ptr(), bases1.stride(0), n, stream)
+        self._check(rc, "spg_qc_device")
+
+    def qc_stats(self):
+        """Accumulated -qc statistics of all devices as a dict (scalars and numpy arrays)."""
+        st = _QcStats()
+        self._check(_lib.spg_qc_stats_get(self._h, C.byref(st)), "spg_qc_stats_get")
+        return qc_stats_to_dict(st)
 
     def set_option(self, option, value):
         self._check(_lib.spg_set_option(self._h, option, value), "spg_set_option")

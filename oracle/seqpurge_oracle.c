@@ -512,3 +512,62 @@ void spo_trim_batch(const spo_params* p, uint8_t* bases1, uint8_t* quals1, uint8
 	free(ts);
 	free(ids);
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * StatisticsReads::update(const FastqEntry&, ReadDirection)  (src/cppNGS/StatisticsReads.cpp:26-81), raw reads
+ * ------------------------------------------------------------------------------------------------------------- */
+
+static void qc_update(const uint8_t* bases, const uint8_t* quals, int cycles, int reverse, spo_qc_stats* s)
+{
+	if (reverse) ++s->reads_reverse; /* :29-36 */
+	else ++s->reads_forward;
+	s->bases_sequenced += cycles; /* :39-41 */
+	if (cycles < SPO_MAXLEN) s->read_lengths[cycles]++;
+	else s->errors++;
+
+	for (int i = 0; i < cycles && i < SPO_MAXLEN; ++i) /* :50, Pileup::inc (src/cppNGS/Pileup.cpp:17-32) */
+	{
+		switch (bases[i])
+		{
+			case 'A': case 'a': s->pileup[i][0]++; break;
+			case 'C': case 'c': s->pileup[i][1]++; break;
+			case 'G': case 'g': s->pileup[i][2]++; break;
+			case 'T': case 't': s->pileup[i][3]++; break;
+			case 'N': case 'n': s->pileup[i][4]++; break;
+			case '-': case '~': break;
+			default: s->errors++; /* the reference throws "Unknown base" */
+		}
+	}
+
+	double q_sum = 0.0; /* :53-70 */
+	for (int i = 0; i < cycles && i < SPO_MAXLEN; ++i)
+	{
+		int q = (int)(signed char)quals[i] - 33; /* FastqEntry::quality(i) with the default offset */
+		q_sum += q;
+		if (q < 0 || q >= 100) /* >= 100 throws in the reference, < 0 indexes base_qualities_ out of bounds */
+		{
+			s->errors++;
+			continue;
+		}
+		if (q >= 20.0) ++s->base_q20;
+		if (q >= 30.0) ++s->base_q30;
+		if (reverse) s->qsum_reverse[i] += q;
+		else s->qsum_forward[i] += q;
+	}
+	double mean_qscore = q_sum / cycles; /* :71-80 */
+	if (isfinite(mean_qscore))
+	{
+		if (mean_qscore >= 20.0) ++s->read_q20;
+	}
+}
+
+void spo_qc_update_batch(const uint8_t* bases1, const uint8_t* quals1, const uint8_t* bases2, const uint8_t* quals2, const uint16_t* len1, const uint16_t* len2,
+                         int stride, int64_t n, spo_qc_stats* out)
+{
+	for (int64_t r = 0; r < n; ++r) /* AnalysisWorker.cpp:86-95 */
+	{
+		size_t off = (size_t)r * (size_t)stride;
+		qc_update(bases1 + off, quals1 + off, len1[r], 0, out);
+		qc_update(bases2 + off, quals2 + off, len2[r], 1, out);
+	}
+}

@@ -76,6 +76,21 @@ typedef struct spo_ecstats
 	int64_t errors_per_read[SPO_MAXLEN];
 } spo_ecstats;
 
+/* accumulators of StatisticsReads::update(const FastqEntry&, ReadDirection) (src/cppNGS/StatisticsReads.cpp:26-81) that the
+   paired-end qcML report uses (StatisticsReads::getResult, :140-330); same layout as spg_qc_stats */
+typedef struct spo_qc_stats
+{
+	int64_t reads_forward, reads_reverse, bases_sequenced, read_q20, base_q20, base_q30, errors;
+	int64_t read_lengths[SPO_MAXLEN];
+	int64_t pileup[SPO_MAXLEN][5]; /* A C G T N */
+	int64_t qsum_forward[SPO_MAXLEN];
+	int64_t qsum_reverse[SPO_MAXLEN];
+} spo_qc_stats;
+
+/* StatisticsReads::update for read 1 (FORWARD) and read 2 (REVERSE) of every pair of a SoA batch, added to *out */
+void spo_qc_update_batch(const uint8_t* bases1, const uint8_t* quals1, const uint8_t* bases2, const uint8_t* quals2, const uint16_t* len1, const uint16_t* len2,
+                         int stride, int64_t n, spo_qc_stats* out);
+
 void spo_default_params(spo_params* p);
 
 /* BasicStatistics::factorial / matchProbability (src/cppCORE/BasicStatistics.cpp:249-307).

@@ -28,6 +28,58 @@ class _SpoEc(C.Structure):
     _fields_ = [("mismatch_r1", C.c_int64 * MAXLEN), ("mismatch_r2", C.c_int64 * MAXLEN), ("errors_per_read", C.c_int64 * MAXLEN)]
 
 
+class _SpoQc(C.Structure):
+    _fields_ = [
+        ("reads_forward", C.c_int64), ("reads_reverse", C.c_int64), ("bases_sequenced", C.c_int64), ("read_q20", C.c_int64),
+        ("base_q20", C.c_int64), ("base_q30", C.c_int64), ("errors", C.c_int64),
+        ("read_lengths", C.c_int64 * MAXLEN), ("pileup", (C.c_int64 * 5) * MAXLEN),
+        ("qsum_forward", C.c_int64 * MAXLEN), ("qsum_reverse", C.c_int64 * MAXLEN),
+    ]
+
+
+def _qc_to_dict(st):
+    d = {k: int(getattr(st, k)) for k in ("reads_forward", "reads_reverse", "bases_sequenced", "read_q20", "base_q20", "base_q30", "errors")}
+    d["read_lengths"] = np.array(st.read_lengths, dtype=np.int64)
+    d["pileup"] = np.array([list(row) for row in st.pileup], dtype=np.int64)
+    d["qsum_forward"] = np.array(st.qsum_forward, dtype=np.int64)
+    d["qsum_reverse"] = np.array(st.qsum_reverse, dtype=np.int64)
+    return d
+
+
+def oracle_qc(batch):
+    """StatisticsReads::update over a Batch (raw reads) by the CPU oracle -> dict."""
+    lib = oracle_lib()
+    st = _SpoQc()
+    lib.spo_qc_update_batch(batch.bases1.ctypes.data, batch.quals1.ctypes.data, batch.bases2.ctypes.data, batch.quals2.ctypes.data,
+                            batch.len1.ctypes.data, batch.len2.ctypes.data, batch.stride, batch.n, C.byref(st))
+    return _qc_to_dict(st)
+
+
+def qc_metrics(d):
+    """The eight paired-end quality parameters of StatisticsReads::getResult (src/cppNGS/StatisticsReads.cpp:140-200) as the strings
+    a qcML file holds (QCValue::toString: integers as such, doubles with two decimals)."""
+    total_reads = d["reads_forward"] + d["reads_reverse"]
+    pile = d["pileup"]
+    c_base_n = int(pile[:, 4].sum())
+    c_base_gc = int(pile[:, 1].sum() + pile[:, 2].sum())
+    bases_total = int(pile.sum())
+    keys = [int(i) for i in np.nonzero(d["read_lengths"])[0]]
+    lengths = ", ".join(str(k) for k in keys) if len(keys) < 4 else f"{keys[0]}-{keys[-1]}"
+    f2 = lambda v: f"{v:.2f}"  # noqa: E731
+    return [
+        ("read count", str(total_reads)),
+        ("read length", lengths),
+        ("bases sequenced (MB)", f2(d["bases_sequenced"] / 1000000.0)),
+        ("Q20 read percentage", f2(100.0 * d["read_q20"] / total_reads)),
+        ("Q20 base percentage", f2(100.0 * d["base_q20"] / bases_total)),
+        ("Q30 base percentage", f2(100.0 * d["base_q30"] / bases_total)),
+        ("no base call percentage", f2(100.0 * c_base_n / bases_total)),
+        ("gc content percentage", f2(100.0 * c_base_gc / (bases_total - c_base_n))),
+    ]
+
+
+
+
 _oracle = None
 
 
@@ -43,6 +95,8 @@ def oracle_lib():
         lib = C.CDLL(path)
         lib.spo_trim_batch.argtypes = [C.POINTER(_SpoParams)] + [C.c_void_p] * 6 + [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
         lib.spo_trim_batch.restype = None
+        lib.spo_qc_update_batch.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int64, C.POINTER(_SpoQc)]
+        lib.spo_qc_update_batch.restype = None
         lib.spo_match_probability.argtypes = [C.c_double, C.c_int, C.c_int]
         lib.spo_match_probability.restype = C.c_double
         lib.spo_factorial.argtypes = [C.c_int]

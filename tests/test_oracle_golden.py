@@ -113,3 +113,37 @@ def test_batch_form_matches_cli_records(oracle_build, tmp_path):
     got2 = [len(r[1]) for r in H.read_fastq(str(out2))]
     assert got1 == rec["len1"].tolist() and got2 == rec["len2"].tolist()
     assert (rec["status"] == 0).all()
+
+
+def _golden_qc_values():
+    import re
+
+    vals = []
+    with open(f"{G}/SeqPurge_out1.qcML", encoding="latin-1") as f:
+        for line in f:
+            m = re.search(r'<qualityParameter ID="qp\d+" name="([^"]+)".* value="([^"]*)"', line)
+            if m:
+                vals.append((m.group(1), m.group(2)))
+    return vals
+
+
+def test_qc_statistics_match_the_reference_qcml():
+    """-qc (SeqPurge_Test.cpp:99-113): the eight quality parameters of the reference's golden qcML from the oracle's restatement of
+    StatisticsReads::update / getResult over the untrimmed reads of test_01."""
+    want = _golden_qc_values()
+    assert len(want) == 8
+    d = H.oracle_qc(H.golden_batch(1, 2))
+    assert d["errors"] == 0
+    assert H.qc_metrics(d) == want
+
+
+def test_qc_statistics_invariants():
+    b = H.random_batch(500, 100, 11, ragged=True, n_runs=0.01)
+    d = H.oracle_qc(b)
+    assert d["reads_forward"] == d["reads_reverse"] == b.n
+    assert d["bases_sequenced"] == int(b.len1.sum()) + int(b.len2.sum()) == int(d["pileup"].sum())
+    assert int(d["read_lengths"].sum()) == 2 * b.n
+    assert d["base_q30"] <= d["base_q20"] <= d["bases_sequenced"]
+    # cycle c is covered by the reads longer than c
+    cover = np.array([(b.len1 > c).sum() + (b.len2 > c).sum() for c in range(b.stride)])
+    assert np.array_equal(d["pileup"].sum(axis=1)[: b.stride], cover)
