@@ -208,6 +208,7 @@ struct Device
 	unsigned long long* d_ec = nullptr; // 3 * SPG_MAXLEN
 	unsigned long long* d_qc = nullptr; // spg::kQcWords accumulators of the -qc statistics
 	int occ[4][3] = {};                 // resident CTAs per SM for NW = 0,5,8,10 x kernel variant (min blocks 2,3,4)
+	int qc_occ[3] = {};                 // same for qc_kernel, NW = 5,8,10
 };
 
 enum SlotState
@@ -397,6 +398,29 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	return SPG_OK;
 }
 
+// the statistics kernel keeps little state in registers, so its occupancy is set by the ring: 3 stages of the trimming kernel's tile
+template <int NW>
+cudaError_t launch_qc_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, int* occ_cache)
+{
+	size_t smem;
+	tile_geometry(a.stride, a.tile_pairs, a.stages, smem);
+	a.stages = 3;
+	smem = (size_t)a.stages * (4 * (size_t)a.tile_pairs * a.stride + 4 * (size_t)a.tile_pairs);
+	if (*occ_cache == 0)
+	{
+		cudaError_t e = cudaFuncSetAttribute(spg::qc_kernel<NW, kCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return e;
+		int n = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::qc_kernel<NW, kCW>, (kCW + 1) * 32, smem);
+		if (e != cudaSuccess) return e;
+		*occ_cache = n < 1 ? 1 : n;
+	}
+	const long long n_tiles = (a.n_pairs + a.tile_pairs - 1) / a.tile_pairs;
+	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * *occ_cache);
+	spg::qc_kernel<NW, kCW><<<grid, (kCW + 1) * 32, smem, stream>>>(a);
+	return cudaGetLastError();
+}
+
 int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, const uint8_t* b2, const uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride,
               long long n, cudaStream_t stream)
 {
@@ -411,16 +435,19 @@ int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, con
 	a.n_pairs = n;
 	a.stride = stride;
 	a.acc = d.d_qc;
-	const long long warps_wanted = std::min<long long>((n + 7) / 8, (long long)d.sm_count * 32); // >= 8 pairs per warp, at most 4 CTAs of 8 warps per SM
-	const int blocks = (int)((warps_wanted + 7) / 8);
+	cudaError_t e = cudaSuccess;
 	switch (nw_for_stride(stride))
 	{
-		case 5: spg::qc_kernel<5><<<blocks, 256, 0, stream>>>(a); break;
-		case 8: spg::qc_kernel<8><<<blocks, 256, 0, stream>>>(a); break;
-		case 10: spg::qc_kernel<10><<<blocks, 256, 0, stream>>>(a); break;
-		default: spg::qc_kernel_generic<<<blocks, 256, 0, stream>>>(a); break;
+		case 5: e = launch_qc_cfg<5>(a, d.sm_count, stream, &d.qc_occ[0]); break;
+		case 8: e = launch_qc_cfg<8>(a, d.sm_count, stream, &d.qc_occ[1]); break;
+		case 10: e = launch_qc_cfg<10>(a, d.sm_count, stream, &d.qc_occ[2]); break;
+		default:
+		{
+			const long long warps_wanted = std::min<long long>((n + 7) / 8, (long long)d.sm_count * 32); // >= 8 pairs per warp, at most 4 CTAs of 8 warps per SM
+			spg::qc_kernel_generic<<<(int)((warps_wanted + 7) / 8), 256, 0, stream>>>(a);
+			e = cudaGetLastError();
+		}
 	}
-	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return fail(ctx, SPG_ERR_CUDA, std::string("qc_kernel launch: ") + cudaGetErrorString(e));
 	std::lock_guard<std::mutex> g(ctx->mu);
 	++ctx->launches;
@@ -649,6 +676,8 @@ int spg_qc_device(spg_ctx* ctx, int device_index, const void* bases1, const void
 	if (device_index < 0 || device_index >= (int)ctx->devs.size()) return fail(ctx, SPG_ERR_PARAM, "device index out of range");
 	if (stride < 16 || stride % 2 != 0 || stride > 1008) return fail(ctx, SPG_ERR_PARAM, "stride must be even and in [16,1008]");
 	if (n_pairs < 0) return fail(ctx, SPG_ERR_PARAM, "negative n_pairs");
+	const uintptr_t bits = (uintptr_t)bases1 | (uintptr_t)quals1 | (uintptr_t)bases2 | (uintptr_t)quals2 | (uintptr_t)len1 | (uintptr_t)len2;
+	if (bits & 15u) return fail(ctx, SPG_ERR_PARAM, "device pointers must be 16-byte aligned");
 	Device& d = ctx->devs[(size_t)device_index];
 	SPG_CUDA(ctx, cudaSetDevice(d.id));
 	return launch_qc(ctx, d, (const uint8_t*)bases1, (const uint8_t*)quals1, (const uint8_t*)bases2, (const uint8_t*)quals2, len1, len2, stride, (long long)n_pairs,

@@ -1,16 +1,19 @@
 // spg_qc.cuh -- raw-read statistics (-qc) of a batch: the accumulators of StatisticsReads::update(FastqEntry, direction) of
 // imgag/ngs-bits (src/cppNGS/StatisticsReads.cpp:26-81) that the paired-end qcML report needs, as one reduction kernel.
 //
-// One warp per read pair (grid-stride), lane l owns the cycles l, 32+l, ...: the per-cycle base counts (A,C,G,T,N) and quality
-// sums live in that lane's registers for the whole launch, so the inner loop has no atomics: per base one table lookup that
-// yields a one-hot 6-bit field (five of them packed in a word, spilled into full counters every 31 pairs) and one for the
-// quality (>=20 / >=30 flags). Per read a warp reduction gives the mean quality. Registers are combined per CTA in shared memory
-// and added to the device-wide 64-bit accumulators at the end.
+// Same skeleton as the trimming kernel (spg_kernel.cuh): persistent CTAs, one producer warp that streams tiles of whole rows into a
+// shared-memory ring with 1-D bulk copies (TMA), CW consumer warps, one warp per read pair, lane l owns the cycles l, 32+l, ...
+// The inner loop has no atomics: per base one table lookup that yields a one-hot 6-bit field (five of them packed in a register
+// per owned cycle) and one lookup for the quality (value, >=20 and >=30 flags in separate bit fields, so that one add per base
+// accumulates the read's quality sum and both counts). Every 31 pairs a warp spills its packed counters into the CTA's table in
+// shared memory; per read a warp reduction gives the mean quality. At the end each CTA adds its table to the device-wide 64-bit
+// accumulators.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/seqpurge_b200.h"
+#include "spg_kernel.cuh"
 
 namespace spg
 {
@@ -33,6 +36,8 @@ struct QcArgs
 	const uint16_t* len2;
 	long long n_pairs;
 	int stride;
+	int tile_pairs; // multiple of 8
+	int stages;     // <= kMaxStages
 	unsigned long long* acc; // [kQcWords]
 };
 
@@ -51,138 +56,190 @@ __device__ __forceinline__ uint32_t qc_base_field(int c) // one-hot 6-bit field 
 		default: return kQcBad;        // the reference throws "Unknown base"
 	}
 }
-__device__ __forceinline__ uint32_t qc_qual_field(int byte) // bit 0: q >= 20, bit 16: q >= 30; StatisticsReads.cpp:53-60
+// bits 0..6: q, bit 12: q >= 20, bit 20: q >= 30 (StatisticsReads.cpp:53-60); up to 15 of them can be added without a carry between fields
+__device__ __forceinline__ uint32_t qc_qual_field(int byte)
 {
 	const int q = (int)(signed char)byte - 33;
 	if (q < 0 || q >= 100) return kQcBad; // q >= 100 throws in the reference, q < 0 indexes out of bounds there
-	return (q >= 20 ? 1u : 0u) | (q >= 30 ? 0x10000u : 0u);
+	return (uint32_t)q | (q >= 20 ? 0x1000u : 0u) | (q >= 30 ? 0x100000u : 0u);
 }
 
-template <int NW>
-__global__ void __launch_bounds__(256) qc_kernel(const __grid_constant__ QcArgs A)
+template <int NW, int CW>
+__global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant__ QcArgs A)
 {
+	constexpr int kThreads = (CW + 1) * 32;
+	extern __shared__ __align__(128) uint8_t smem[];
+	__shared__ __align__(8) uint64_t full_bar[kMaxStages];
+	__shared__ __align__(8) uint64_t empty_bar[kMaxStages];
 	__shared__ uint32_t lutb[256], lutq[256];
 	__shared__ uint32_t s_len[SPG_MAXLEN];
-	__shared__ uint32_t s_acc[NW * 32 * 7]; // [cycle][A,C,G,T,N,qsum_f,qsum_r] of this CTA
+	__shared__ uint32_t s_acc[7][NW * 32]; // [A,C,G,T,N,qsum_f,qsum_r][cycle] of this CTA
 	__shared__ unsigned long long s_scalar[8];
 
-	for (int i = threadIdx.x; i < 256; i += blockDim.x)
+	const int warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31;
+	const int TP = A.tile_pairs;
+	const uint32_t plane_bytes = (uint32_t)TP * (uint32_t)A.stride;
+	const uint32_t stage_bytes = 4u * plane_bytes + 4u * (uint32_t)TP;
+	const long long n_tiles = (A.n_pairs + TP - 1) / TP;
+	const uint32_t smem_base = smem_u32(smem);
+
+	for (int i = threadIdx.x; i < 256; i += kThreads)
 	{
 		lutb[i] = qc_base_field(i);
 		lutq[i] = qc_qual_field(i);
 	}
-	for (int i = threadIdx.x; i < SPG_MAXLEN; i += blockDim.x) s_len[i] = 0;
-	for (int i = threadIdx.x; i < NW * 32 * 7; i += blockDim.x) s_acc[i] = 0;
+	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads) s_len[i] = 0;
+	for (int i = threadIdx.x; i < 7 * NW * 32; i += kThreads) (&s_acc[0][0])[i] = 0;
 	if (threadIdx.x < 8) s_scalar[threadIdx.x] = 0;
+	if (threadIdx.x == 0)
+	{
+		for (int s = 0; s < A.stages; ++s)
+		{
+			mbar_init(&full_bar[s], 1);
+			mbar_init(&empty_bar[s], CW);
+		}
+		fence_barrier_init();
+	}
 	__syncthreads();
 
-	const int lane = threadIdx.x & 31;
-	const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-
-	uint32_t cnt[NW][5], pk[NW], qsum[2][NW];
-#pragma unroll
-	for (int w = 0; w < NW; ++w)
+	if (warp == CW)
 	{
-		pk[w] = 0;
-		qsum[0][w] = qsum[1][w] = 0;
-#pragma unroll
-		for (int k = 0; k < 5; ++k) cnt[w][k] = 0;
-	}
-	uint32_t c20 = 0, c30 = 0, bad = 0;
-	unsigned long long reads[2] = {0, 0}, bases = 0, rq20 = 0; // warp-uniform, kept by every lane, reported by lane 0
-	int since_flush = 0;
-
-	for (long long r = gwarp; r < A.n_pairs; r += nwarps)
-	{
-#pragma unroll
-		for (int rd = 0; rd < 2; ++rd)
+		// ===== producer: one lane issues the bulk copies of each tile (same tile layout as trim_kernel) =====
+		if (lane == 0)
 		{
-			const uint8_t* brow = (rd ? A.b2 : A.b1) + (size_t)r * A.stride;
-			const uint8_t* qrow = (rd ? A.q2 : A.q1) + (size_t)r * A.stride;
-			int len = rd ? A.len2[r] : A.len1[r];
-			if (len > A.stride || len >= SPG_MAXLEN)
+			int it = 0;
+			for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it)
 			{
-				bad = kQcBad;
-				len = min(len, A.stride); // stay inside the row
+				const int s = it % A.stages;
+				const uint32_t round = (uint32_t)(it / A.stages);
+				if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1u);
+				const long long first = t * TP;
+				const int cnt = (int)min((long long)TP, A.n_pairs - first);
+				const uint32_t row_bytes = ((uint32_t)cnt * (uint32_t)A.stride + 15u) & ~15u;
+				const uint32_t len_bytes = (uint32_t)((cnt + 7) / 8) * 16u;
+				const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+				mbar_arrive_expect_tx(&full_bar[s], 4 * row_bytes + 2 * len_bytes);
+				const size_t goff = (size_t)first * A.stride;
+				bulk_g2s(st + 0 * plane_bytes, A.b1 + goff, row_bytes, &full_bar[s]);
+				bulk_g2s(st + 1 * plane_bytes, A.q1 + goff, row_bytes, &full_bar[s]);
+				bulk_g2s(st + 2 * plane_bytes, A.b2 + goff, row_bytes, &full_bar[s]);
+				bulk_g2s(st + 3 * plane_bytes, A.q2 + goff, row_bytes, &full_bar[s]);
+				bulk_g2s(st + 4 * plane_bytes, A.len1 + first, len_bytes, &full_bar[s]);
+				bulk_g2s(st + 4 * plane_bytes + 2u * (uint32_t)TP, A.len2 + first, len_bytes, &full_bar[s]);
 			}
-			uint32_t pq = 0;
-			int rsum = 0;
-#pragma unroll
-			for (int w = 0; w < NW; ++w)
-			{
-				const int pos = 32 * w + lane;
-				if (pos < len)
-				{
-					const uint32_t b = brow[pos], q = qrow[pos];
-					const uint32_t vb = lutb[b], vq = lutq[q];
-					bad |= vb | vq;
-					pk[w] += vb & 0x3FFFFFFFu;
-					pq += vq & 0x00010001u;
-					const int qv = (int)(signed char)q - 33;
-					qsum[rd][w] += (uint32_t)qv;
-					rsum += qv;
-				}
-			}
-			c20 += pq & 0xFFFFu;
-			c30 += pq >> 16;
-			const int total = __reduce_add_sync(0xffffffffu, rsum);
-			// mean_qscore = q_sum/cycles >= 20.0 (only if cycles > 0: 0/0 is not a valid float there)
-			if (len > 0 && total >= 20 * len) ++rq20;
-			++reads[rd];
-			bases += (unsigned long long)len;
-			if (lane == 0 && len < SPG_MAXLEN) atomicAdd(&s_len[len], 1u);
 		}
-		if (++since_flush == 31) // 2 reads x 31 pairs = 62 < 64: the 6-bit fields cannot overflow
-		{
+	}
+	else
+	{
+		// ===== consumers =====
+		uint32_t pk[NW], qs[NW]; // per owned cycle: five 6-bit base counters; quality sums (forward | reverse << 16)
+#pragma unroll
+		for (int w = 0; w < NW; ++w) pk[w] = qs[w] = 0;
+		uint32_t c20 = 0, c30 = 0, bad = 0;
+		unsigned long long bases = 0;
+		uint32_t reads = 0, rq20 = 0; // warp-uniform, reported by lane 0
+		int since_flush = 0;
+
+		auto flush = [&]() {
 #pragma unroll
 			for (int w = 0; w < NW; ++w)
 			{
+				const int cyc = 32 * w + lane;
 #pragma unroll
-				for (int k = 0; k < 5; ++k) cnt[w][k] += (pk[w] >> (6 * k)) & 63u;
-				pk[w] = 0;
+				for (int k = 0; k < 5; ++k)
+				{
+					const uint32_t v = (pk[w] >> (6 * k)) & 63u;
+					if (v) atomicAdd(&s_acc[k][cyc], v);
+				}
+				const uint32_t f = qs[w] & 0xFFFFu, r = qs[w] >> 16;
+				if (f) atomicAdd(&s_acc[5][cyc], f);
+				if (r) atomicAdd(&s_acc[6][cyc], r);
+				pk[w] = qs[w] = 0;
 			}
 			since_flush = 0;
+		};
+
+		int it = 0;
+		for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it)
+		{
+			const int s = it % A.stages;
+			const uint32_t round = (uint32_t)(it / A.stages);
+			mbar_wait(&full_bar[s], round & 1u);
+			const long long first = t * TP;
+			const int cnt = (int)min((long long)TP, A.n_pairs - first);
+			const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
+			const uint32_t lens = st + 4 * plane_bytes;
+			for (int pr = warp; pr < cnt; pr += CW)
+			{
+				const uint32_t roff = (uint32_t)pr * (uint32_t)A.stride;
+#pragma unroll
+				for (int rd = 0; rd < 2; ++rd)
+				{
+					const uint32_t rb = st + (uint32_t)(2 * rd) * plane_bytes + roff, rq = rb + plane_bytes;
+					int len = (int)lds_u16(lens + 2u * (uint32_t)(rd * TP + pr));
+					bases += (unsigned long long)len;
+					if (lane == 0 && len < SPG_MAXLEN) atomicAdd(&s_len[len], 1u);
+					if (len > A.stride || len >= SPG_MAXLEN)
+					{
+						bad = kQcBad;
+						len = min(len, A.stride); // stay inside the row
+					}
+					uint32_t racc = 0;
+#pragma unroll
+					for (int w = 0; w < NW; ++w)
+					{
+						const int pos = 32 * w + lane;
+						if (pos < len)
+						{
+							const uint32_t vb = lutb[lds_u8(rb + pos)], vq = lutq[lds_u8(rq + pos)];
+							bad |= vb | vq; // only bit 31 is looked at
+							pk[w] += vb;    // a bad base adds bit 31, which no field uses
+							racc += vq;
+							qs[w] += (vq & 0x7Fu) << (16 * rd);
+						}
+					}
+					c20 += (racc >> 12) & 0xFu;
+					c30 += (racc >> 20) & 0xFu;
+					const int total = __reduce_add_sync(kFull, (int)(racc & 0xFFFu));
+					// mean_qscore = q_sum/cycles >= 20.0 (only if cycles > 0: 0/0 is not a valid float there)
+					if (len > 0 && total >= 20 * len) ++rq20;
+				}
+				++reads;
+				if (++since_flush == 31) flush(); // 2 reads x 31 pairs = 62 < 64: the 6-bit fields cannot overflow
+			}
+			__syncwarp();
+			if (lane == 0)
+			{
+				fence_proxy_async();
+				mbar_arrive(&empty_bar[s]);
+			}
+		}
+		flush();
+		const unsigned long long t20 = __reduce_add_sync(kFull, c20), t30 = __reduce_add_sync(kFull, c30);
+		const bool any_bad = __any_sync(kFull, (bad & kQcBad) != 0);
+		if (lane == 0)
+		{
+			atomicAdd(&s_scalar[kQcReadsF], (unsigned long long)reads);
+			atomicAdd(&s_scalar[kQcReadsR], (unsigned long long)reads);
+			atomicAdd(&s_scalar[kQcBases], bases);
+			atomicAdd(&s_scalar[kQcReadQ20], (unsigned long long)rq20);
+			atomicAdd(&s_scalar[kQcBaseQ20], t20);
+			atomicAdd(&s_scalar[kQcBaseQ30], t30);
+			if (any_bad) atomicAdd(&s_scalar[kQcErrors], 1ull);
 		}
 	}
-#pragma unroll
-	for (int w = 0; w < NW; ++w)
-#pragma unroll
-		for (int k = 0; k < 5; ++k) cnt[w][k] += (pk[w] >> (6 * k)) & 63u;
-
-	// combine the warps of this CTA in shared memory, then one 64-bit atomic per CTA and counter
-#pragma unroll
-	for (int w = 0; w < NW; ++w)
-	{
-		uint32_t* row = &s_acc[(32 * w + lane) * 7];
-#pragma unroll
-		for (int k = 0; k < 5; ++k)
-			if (cnt[w][k]) atomicAdd(&row[k], cnt[w][k]);
-		if (qsum[0][w]) atomicAdd(&row[5], qsum[0][w]);
-		if (qsum[1][w]) atomicAdd(&row[6], qsum[1][w]);
-	}
-	const unsigned long long t20 = __reduce_add_sync(0xffffffffu, c20), t30 = __reduce_add_sync(0xffffffffu, c30);
-	const bool any_bad = __any_sync(0xffffffffu, (bad & kQcBad) != 0);
-	if (lane == 0)
-	{
-		atomicAdd(&s_scalar[kQcReadsF], reads[0]);
-		atomicAdd(&s_scalar[kQcReadsR], reads[1]);
-		atomicAdd(&s_scalar[kQcBases], bases);
-		atomicAdd(&s_scalar[kQcReadQ20], rq20);
-		atomicAdd(&s_scalar[kQcBaseQ20], t20);
-		atomicAdd(&s_scalar[kQcBaseQ30], t30);
-		if (any_bad) atomicAdd(&s_scalar[kQcErrors], 1ull);
-	}
 	__syncthreads();
+
+	// one 64-bit atomic per CTA and non-zero counter
 	if (threadIdx.x < 8 && s_scalar[threadIdx.x]) atomicAdd(&A.acc[threadIdx.x], s_scalar[threadIdx.x]);
-	for (int i = threadIdx.x; i < SPG_MAXLEN; i += blockDim.x)
+	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads)
 		if (s_len[i]) atomicAdd(&A.acc[kQcLen + i], (unsigned long long)s_len[i]);
-	for (int i = threadIdx.x; i < NW * 32 * 7; i += blockDim.x)
+	for (int i = threadIdx.x; i < 7 * NW * 32; i += kThreads)
 	{
-		const uint32_t v = s_acc[i];
-		if (!v) continue;
-		const int cycle = i / 7, k = i % 7;
-		if (cycle >= SPG_MAXLEN) continue;
+		const int k = i / (NW * 32), cycle = i % (NW * 32);
+		const uint32_t v = s_acc[k][cycle];
+		if (!v || cycle >= SPG_MAXLEN) continue;
 		if (k < 5) atomicAdd(&A.acc[kQcPile + 5 * cycle + k], (unsigned long long)v);
 		else atomicAdd(&A.acc[(k == 5 ? kQcQf : kQcQr) + cycle], (unsigned long long)v);
 	}
@@ -217,8 +274,8 @@ __global__ void __launch_bounds__(256) qc_kernel_generic(const __grid_constant__
 				const int qv = (int)(signed char)qrow[pos] - 33;
 				atomicAdd(&A.acc[(rd ? kQcQr : kQcQf) + pos], (unsigned long long)qv);
 				rsum += qv;
-				n20 += vq & 1u;
-				n30 += (vq >> 16) & 1u;
+				n20 += (vq >> 12) & 1u;
+				n30 += (vq >> 20) & 1u;
 			}
 			const int total = __reduce_add_sync(0xffffffffu, rsum);
 			const int t20 = __reduce_add_sync(0xffffffffu, n20), t30 = __reduce_add_sync(0xffffffffu, n30);

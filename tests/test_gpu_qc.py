@@ -64,7 +64,7 @@ def qc_via_device(sp, batch):  # noqa: F811
     l1 = torch.from_numpy(batch.len1.view(np.int16)).to(dev)
     l2 = torch.from_numpy(batch.len2.view(np.int16)).to(dev)
     eng = sp.Engine(sp.TrimmingParameters(qc=True), devices=(0,))
-    eng.qc_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
+    eng.qc_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, n_pairs=batch.n)  # Batch rows are padded to a multiple of 8
     got = eng.qc_stats()
     eng.close()
     return got
