@@ -159,6 +159,67 @@ const char* spg_last_error(spg_ctx* ctx);
 /* Replaces: ~ThreadCoordinator. Waits for queued work, frees everything. */
 void spg_destroy(spg_ctx* ctx);
 
+/* ---- FASTQ text in, FASTQ text out ------------------------------------------------------------------
+ * Replaces, around the trimming path: the line splitting of FastqFileStream::readEntry (src/cppNGS/FastqFileStream.cpp:135-160 over
+ * VersatileFile::readLine, src/cppCORE/VersatileFile.cpp:274-399), the AoS->SoA flattening of the worker, the routing of
+ * OutputWorker::run (src/SeqPurge/OutputWorker.cpp:36-57) and the record layout of FastqOutfileStream::write
+ * (src/cppNGS/FastqFileStream.cpp:183-198), plus the adapter-consensus counters of AnalysisWorker.cpp:279-290. The host only
+ * inflates the inputs into the slot's text buffers and deflates the output text.
+ *
+ * A text chunk must start at a record start; it may end anywhere. spg_fq_wait reports how many bytes of each chunk belong to the
+ * pairs that were processed: the caller moves the rest to the front of the next chunk of that file. */
+typedef struct spg_fq spg_fq;
+
+typedef struct spg_fq_config
+{
+	int32_t n_slots;   /* chunks in flight; slot s runs on device s % n_devices of the context */
+	int32_t max_pairs; /* pairs per chunk at most */
+	int32_t max_len;   /* longest read the rows can take (< 1000); spg_fq_output.max_len tells when a chunk needs more */
+	int64_t text_cap;  /* bytes of text per file and chunk */
+	int32_t min_len;   /* -min_len: reads shorter than this after trimming are dropped (OutputWorker.cpp:41-56) */
+	int32_t singles;   /* 1: -out3 given, reads whose mate was dropped go to out[2] (read 1) / out[3] (read 2) */
+} spg_fq_config;
+
+typedef struct spg_fq_input
+{
+	uint8_t* text1; /* pinned host buffers of text_cap bytes */
+	uint8_t* text2;
+	int64_t cap;
+} spg_fq_input;
+
+/* framing status of a pair (spg_fq_output.frame_status) */
+#define SPG_FQ_OK 0
+#define SPG_FQ_HEADER_MISMATCH 1 /* "Headers of reads do not match" (AnalysisWorker.cpp:110-120) */
+#define SPG_FQ_LENGTH_MISMATCH 2 /* |bases| != |qualities| */
+#define SPG_FQ_TOO_LONG 3        /* read longer than max_len of this stream (or >= 1000) */
+
+typedef struct spg_fq_output
+{
+	int32_t n_pairs;             /* pairs processed = min(records1, records2, max_pairs) */
+	int32_t records1, records2;  /* records found in the two chunks */
+	int64_t consumed1, consumed2; /* bytes of the chunks that belong to the processed pairs */
+	const uint8_t* out[4];       /* out1, out2, out3 (read-1 singletons), out4 (read-2 singletons): FASTQ text, pinned host memory */
+	int64_t out_bytes[4];
+	const spg_result* results;   /* [n_pairs] as spg_wait */
+	const uint16_t* len1;        /* [n_pairs] untrimmed lengths */
+	const uint16_t* len2;
+	const uint8_t* frame_status; /* [n_pairs] SPG_FQ_* */
+	int32_t error_pair;          /* first pair with frame_status != 0 or results[].status != 0, or -1 */
+	int32_t max_len;             /* longest bases/qualities line of the chunk */
+} spg_fq_output;
+
+/* Attaches a FASTQ stream to a context (which provides parameters, tables, devices; it may have been created with n_slots = 0). */
+int spg_fq_open(spg_ctx* ctx, const spg_fq_config* cfg, spg_fq** out);
+int spg_fq_buffers(spg_fq* fq, int slot, spg_fq_input* in);
+/* Queues: H2D of the two chunks, framing, [-qc statistics], trimming, output assembly, D2H. final1/final2: the chunk holds the end
+   of its file (an unterminated last line and an incomplete last record then count, as for the reference's reader). */
+int spg_fq_submit(spg_fq* fq, int slot, int64_t bytes1, int64_t bytes2, int final1, int final2);
+int spg_fq_wait(spg_fq* fq, int slot, spg_fq_output* out);
+/* Adapter-consensus counters of all chunks so far: counts[read][position 0..39][A,C,G,T,N]; *unknown_base != 0 if a base outside
+   ACGTN (and '-', '~') was met, where the reference's Pileup::inc throws. */
+int spg_fq_consensus_get(spg_fq* fq, int64_t counts[2][40][5], int32_t* unknown_base);
+void spg_fq_close(spg_fq* fq);
+
 /* ---- tuning / introspection (not part of the reference seam) ------------------------------------------------------------ */
 
 #define SPG_OPT_FORCE_BYTEWISE 1 /* value 1: route every pair through the byte-wise kernel path (cross-check of the bit-plane path) */

@@ -18,6 +18,7 @@
 
 #include "spg_kernel.cuh"
 #include "spg_qc.cuh"
+#include "spg_fastq.cuh"
 
 namespace
 {
@@ -232,6 +233,11 @@ struct Slot
 
 } // namespace
 
+namespace
+{
+void fq_free(spg_fq* fq); // spg_fastq_engine.inc
+}
+
 struct spg_ctx
 {
 	spg_params params;
@@ -251,6 +257,7 @@ struct spg_ctx
 	int tile_pairs = 0; // 0 = automatic
 	int stages = 0;     // 0 = automatic
 	long long launches = 0;
+	std::vector<spg_fq*> fqs; // FASTQ streams attached to this context (closed by spg_destroy if the caller did not)
 };
 
 namespace
@@ -318,12 +325,14 @@ cudaError_t launch_nw(const spg::KArgs& a, int minb, int sm_count, int ctas_per_
 	}
 }
 
+// n_dev: optional device pointer to the actual pair count (<= n); n then sizes the grid only
 int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride, long long n,
-                spg_result* out, cudaStream_t stream)
+                spg_result* out, cudaStream_t stream, const int* n_dev = nullptr)
 {
 	if (n <= 0) return SPG_OK;
 	spg::KArgs a;
 	memset(&a, 0, sizeof(a));
+	a.n_dev = n_dev;
 	a.b1 = b1;
 	a.q1 = q1;
 	a.b2 = b2;
@@ -422,10 +431,11 @@ cudaError_t launch_qc_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, int
 }
 
 int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, const uint8_t* b2, const uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride,
-              long long n, cudaStream_t stream)
+              long long n, cudaStream_t stream, const int* n_dev = nullptr)
 {
 	if (n <= 0) return SPG_OK;
 	spg::QcArgs a;
+	a.n_dev = n_dev;
 	a.b1 = b1;
 	a.q1 = q1;
 	a.b2 = b2;
@@ -722,6 +732,7 @@ const char* spg_last_error(spg_ctx* ctx)
 void spg_destroy(spg_ctx* ctx)
 {
 	if (!ctx) return;
+	while (!ctx->fqs.empty()) fq_free(ctx->fqs.back());
 	for (Slot& sl : ctx->slots)
 	{
 		if (sl.dev < (int)ctx->devs.size() && ctx->devs[(size_t)sl.dev].id >= 0) cudaSetDevice(ctx->devs[(size_t)sl.dev].id);
@@ -787,3 +798,5 @@ int64_t spg_launch_count(spg_ctx* ctx)
 }
 
 } // extern "C"
+
+#include "spg_fastq_engine.inc"

@@ -1,0 +1,576 @@
+// spg_fastq.cuh -- FASTQ framing and output assembly on the device.
+//
+// The host hands over inflated FASTQ text of the two input files (any cut: a chunk starts at a record start and may end anywhere).
+// The kernels below do what FastqFileStream::readEntry (src/cppNGS/FastqFileStream.cpp:135-160, over VersatileFile::readLine,
+// src/cppCORE/VersatileFile.cpp:274-399: a line ends at '\n', trailing '\n'/'\r' are chopped, four lines make an entry, no
+// validation) and the AoS->SoA flattening in front of the trimming kernel do, then -- behind the trimming kernel -- what
+// OutputWorker::run + FastqOutfileStream::write do (src/SeqPurge/OutputWorker.cpp:36-57, FastqFileStream.cpp:183-198): route every
+// pair by the trimmed lengths (both >= min_len -> out1/out2; one -> out3/out4 singleton files, if given; else dropped) and lay the
+// records out as text "header\nbases\nheader2\nqualities\n" in submission order. The adapter-consensus counters of
+// AnalysisWorker.cpp:279-290 are reduced in the same pass.
+//
+//   fq_count_newlines -> fq_scan_counts -> fq_scatter_newlines     line index of both texts (positions of '\n')
+//   fq_plan                                                        records per file, pairs of this batch, bytes consumed
+//   fq_pack                                                        rows + lengths for the trimming kernel, header check (a3)
+//   [qc_kernel] trim_kernel                                        (spg_qc.cuh, spg_kernel.cuh; pair count read from the plan)
+//   fq_out_sizes -> fq_out_scan -> fq_out_write                    output text of the four streams, consensus counters
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/seqpurge_b200.h"
+
+namespace spg
+{
+
+constexpr int kFqBlockThreads = 256;
+constexpr int kFqBytesPerThread = 64;                                   // four 16-byte loads
+constexpr int kFqBlockBytes = kFqBlockThreads * kFqBytesPerThread;      // 16 KiB of text per CTA
+constexpr int kFqOutPairs = 256;                                        // pairs per CTA in the output kernels
+
+// per-pair framing status (first failing check in the order of the reference's worker)
+enum : uint8_t
+{
+	FQ_OK = 0,
+	FQ_HEADER_MISMATCH = 1, // AnalysisWorker.cpp:110-120
+	FQ_LENGTH_MISMATCH = 2, // |bases| != |qualities|
+	FQ_TOO_LONG = 3         // longer than the row stride of this engine (or >= MAXLEN)
+};
+
+struct FqRec // where the two header lines of a record are in the text
+{
+	uint32_t hs, hl;   // start offset and length (without line ending) of the header line
+	uint32_t h2s, h2l; // same for header2
+};
+
+struct FqPlan // device-resident per slot; copied to the host after the batch
+{
+	int n_pairs;
+	int lines[2];        // lines of each text that take part (complete lines; + the unterminated last line of a final chunk)
+	int records[2];      // records available in each text
+	uint32_t consumed[2]; // bytes of each text that belong to the n_pairs records
+	uint32_t out_bytes[4];
+	int err_pair;        // smallest pair index with a framing status != 0, or INT_MAX
+	int max_len;         // longest bases/qualities line seen in the batch
+	int acons_error;     // a base outside ACGTN in the consensus window (Pileup::inc throws there)
+	int pad;
+};
+
+struct FqArgs
+{
+	const uint8_t* text[2];
+	uint32_t bytes[2];
+	int final_[2];       // the text holds the end of its file
+	uint32_t* nl[2];     // [nl_cap] positions of the line ends
+	int nl_cap;
+	uint32_t* block_counts[2]; // [n_blocks] newline count per 16 KiB block, then exclusive offsets
+	int n_blocks[2];
+	int max_pairs;
+	FqPlan* plan;
+	// rows for the trimming kernel
+	uint8_t* rows[4]; // b1, q1, b2, q2
+	uint16_t* len[2];
+	int stride;
+	FqRec* rec[2];
+	uint8_t* fstat;   // [max_pairs]
+	// output
+	const spg_result* res;
+	uint8_t* out[4];  // out1, out2, out3 (read 1 singletons), out4 (read 2 singletons)
+	uint32_t* out_block[4]; // [n_out_blocks] per-CTA byte counts, then exclusive offsets
+	int min_len;
+	int singles;      // -out3 given
+	unsigned long long* acons; // [2][40][5] A,C,G,T,N
+};
+
+__device__ __forceinline__ uint32_t fq_newline_flags(uint32_t w) // bit 7 of every byte that equals '\n' (exact, no borrow artefacts)
+{
+	const uint32_t x = w ^ 0x0A0A0A0Au;
+	const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+	return ~(t | x | 0x7F7F7F7Fu);
+}
+
+// newline flags of the 64 bytes a thread owns: bit i of the result = byte i is '\n' (bytes at or beyond `bytes` never are)
+__device__ __forceinline__ unsigned long long fq_thread_flags(const uint8_t* text, uint32_t bytes, uint32_t base)
+{
+	unsigned long long flags = 0;
+	if (base >= bytes) return 0;
+#pragma unroll
+	for (int v = 0; v < 4; ++v)
+	{
+		const uint32_t off = base + 16u * v;
+		if (off >= bytes) break;
+		const uint4 q = *reinterpret_cast<const uint4*>(text + off); // the buffers are padded to a multiple of 16 bytes
+		const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+		{
+			uint32_t f = fq_newline_flags(w[k]); // bits 7, 15, 23, 31
+			// gather to 4 bits: byte j -> bit j
+			f = ((f >> 7) & 1u) | ((f >> 14) & 2u) | ((f >> 21) & 4u) | ((f >> 28) & 8u);
+			flags |= (unsigned long long)f << (16 * v + 4 * k);
+		}
+	}
+	const uint32_t left = bytes - base;
+	if (left < 64u) flags &= (1ull << left) - 1ull;
+	return flags;
+}
+
+// grid: (max blocks of the two texts, 2)
+__global__ void __launch_bounds__(kFqBlockThreads) fq_count_newlines(const __grid_constant__ FqArgs A)
+{
+	const int f = blockIdx.y;
+	if ((int)blockIdx.x >= A.n_blocks[f]) return;
+	const uint32_t base = (uint32_t)blockIdx.x * kFqBlockBytes + (uint32_t)threadIdx.x * kFqBytesPerThread;
+	int c = __popcll(fq_thread_flags(A.text[f], A.bytes[f], base));
+	c = __reduce_add_sync(0xffffffffu, c);
+	__shared__ int s[kFqBlockThreads / 32];
+	if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		int t = 0;
+		for (int i = 0; i < kFqBlockThreads / 32; ++i) t += s[i];
+		A.block_counts[f][blockIdx.x] = (uint32_t)t;
+	}
+}
+
+// grid: 2 CTAs (one per text) of 1024 threads: exclusive scan of the block counts in place; the plan gets the line totals
+__global__ void __launch_bounds__(1024) fq_scan_counts(const __grid_constant__ FqArgs A)
+{
+	const int f = blockIdx.x;
+	const int n = A.n_blocks[f];
+	__shared__ uint32_t warp_sums[32];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < n; base += 1024)
+	{
+		const int i = base + (int)threadIdx.x;
+		const uint32_t v = i < n ? A.block_counts[f][i] : 0u;
+		uint32_t x = v;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+			if ((int)(threadIdx.x & 31) >= d) x += y;
+		}
+		if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+		__syncthreads();
+		if (threadIdx.x < 32)
+		{
+			uint32_t w = warp_sums[threadIdx.x];
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1)
+			{
+				const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+				if ((int)threadIdx.x >= d) w += y;
+			}
+			warp_sums[threadIdx.x] = w; // inclusive
+		}
+		__syncthreads();
+		const uint32_t before = carry + (threadIdx.x >= 32 ? warp_sums[(threadIdx.x >> 5) - 1] : 0u) + x - v;
+		if (i < n) A.block_counts[f][i] = before;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry = before + v;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+	{
+		// complete lines, plus the unterminated last line of a file's final chunk (readLine returns it like any other line)
+		long long lines = carry;
+		const uint32_t bytes = A.bytes[f];
+		if (A.final_[f] && bytes > 0 && A.text[f][bytes - 1] != '\n') lines += 1;
+		A.plan->lines[f] = (int)min(lines, (long long)A.nl_cap);
+	}
+}
+
+// same grid as fq_count_newlines: positions of the newlines in rank order
+__global__ void __launch_bounds__(kFqBlockThreads) fq_scatter_newlines(const __grid_constant__ FqArgs A)
+{
+	const int f = blockIdx.y;
+	if ((int)blockIdx.x >= A.n_blocks[f]) return;
+	const uint32_t base = (uint32_t)blockIdx.x * kFqBlockBytes + (uint32_t)threadIdx.x * kFqBytesPerThread;
+	unsigned long long flags = fq_thread_flags(A.text[f], A.bytes[f], base);
+	const int c = __popcll(flags);
+	// exclusive scan of the per-thread counts inside the CTA
+	int x = c;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1)
+	{
+		const int y = __shfl_up_sync(0xffffffffu, x, d);
+		if ((int)(threadIdx.x & 31) >= d) x += y;
+	}
+	__shared__ int s[kFqBlockThreads / 32];
+	if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = x;
+	__syncthreads();
+	int before = x - c;
+	for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) before += s[w];
+	uint32_t rank = A.block_counts[f][blockIdx.x] + (uint32_t)before;
+	uint32_t* nl = A.nl[f];
+	while (flags)
+	{
+		const int b = __ffsll((long long)flags) - 1;
+		flags &= flags - 1;
+		if (rank < (uint32_t)A.nl_cap) nl[rank] = base + (uint32_t)b;
+		++rank;
+	}
+	// the virtual line end of an unterminated final line
+	if (blockIdx.x == 0 && threadIdx.x == 0)
+	{
+		const uint32_t bytes = A.bytes[f];
+		if (A.final_[f] && bytes > 0 && A.text[f][bytes - 1] != '\n')
+		{
+			// its rank is the number of real newlines = exclusive offset of the last block + that block's count; recomputed here from
+			// the last block to stay independent of the other CTAs' progress
+			const int lb = A.n_blocks[f] - 1;
+			uint32_t cnt = 0;
+			const uint32_t lbase = (uint32_t)lb * kFqBlockBytes;
+			for (uint32_t i = lbase; i < bytes; ++i) cnt += A.text[f][i] == '\n';
+			const uint32_t r = A.block_counts[f][lb] + cnt;
+			if (r < (uint32_t)A.nl_cap) nl[r] = bytes;
+		}
+	}
+}
+
+// one thread: how many records each text holds, how many pairs this batch gets, how many bytes they cover
+__global__ void fq_plan(const __grid_constant__ FqArgs A)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	FqPlan& P = *A.plan;
+	int rec[2];
+	for (int f = 0; f < 2; ++f)
+	{
+		const int lines = P.lines[f];
+		// a final chunk: the last record may lack lines (readLine returns empty strings at the end of the file) -- ceil
+		rec[f] = A.final_[f] ? (lines + 3) / 4 : lines / 4;
+		P.records[f] = rec[f];
+	}
+	int n = min(min(rec[0], rec[1]), A.max_pairs);
+	P.n_pairs = n;
+	for (int f = 0; f < 2; ++f)
+	{
+		const long long last_line = 4ll * n - 1; // its end closes the n-th record
+		uint32_t c;
+		if (n == 0) c = 0;
+		else if (last_line < P.lines[f]) c = min(A.nl[f][last_line] + 1u, A.bytes[f]);
+		else c = A.bytes[f]; // the final, incomplete record
+		P.consumed[f] = c;
+	}
+	for (int k = 0; k < 4; ++k) P.out_bytes[k] = 0;
+	P.err_pair = 0x7fffffff;
+	P.max_len = 0;
+	P.acons_error = 0;
+}
+
+struct FqLine
+{
+	uint32_t s, e; // [s, e) without line ending
+};
+// line k of text f: from the end of line k-1 to its own end, trailing '\r' chopped; lines beyond the last one are empty
+__device__ __forceinline__ FqLine fq_line(const FqArgs& A, int f, long long k, int lines)
+{
+	FqLine L;
+	if (k >= lines)
+	{
+		L.s = L.e = A.bytes[f];
+		return L;
+	}
+	const uint32_t* nl = A.nl[f];
+	L.s = k == 0 ? 0u : nl[k - 1] + 1u;
+	L.e = nl[k];
+	const uint8_t* t = A.text[f];
+	while (L.e > L.s && t[L.e - 1] == '\r') --L.e;
+	return L;
+}
+
+// first ' ' of a line (or its length): warp-cooperative
+__device__ __forceinline__ uint32_t fq_token_len(const uint8_t* t, FqLine L, int lane)
+{
+	const uint32_t len = L.e - L.s;
+	for (uint32_t base = 0; base < len; base += 32)
+	{
+		const uint32_t i = base + (uint32_t)lane;
+		const uint32_t m = __ballot_sync(0xffffffffu, i < len && t[L.s + i] == ' ');
+		if (m) return base + (uint32_t)(__ffs((int)m) - 1);
+	}
+	return len;
+}
+
+// one warp per pair: rows, lengths, header locations, header check
+__global__ void __launch_bounds__(256) fq_pack(const __grid_constant__ FqArgs A)
+{
+	const int lane = threadIdx.x & 31;
+	const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+	const int n = A.plan->n_pairs;
+	int max_len = 0;
+	for (long long p = gwarp; p < n; p += nwarps)
+	{
+		uint8_t st = FQ_OK;
+		FqLine hdr[2];
+		for (int f = 0; f < 2; ++f)
+		{
+			const int lines = A.plan->lines[f];
+			const uint8_t* t = A.text[f];
+			hdr[f] = fq_line(A, f, 4 * p, lines);
+			const FqLine b = fq_line(A, f, 4 * p + 1, lines);
+			const FqLine h2 = fq_line(A, f, 4 * p + 2, lines);
+			const FqLine q = fq_line(A, f, 4 * p + 3, lines);
+			const uint32_t lb = b.e - b.s, lq = q.e - q.s;
+			max_len = max(max_len, (int)min(max(lb, lq), 0x7fffffffu));
+			uint32_t len = lb;
+			if (lb != lq && st == FQ_OK) st = FQ_LENGTH_MISMATCH;
+			if ((lb > (uint32_t)A.stride || lq > (uint32_t)A.stride || lb >= (uint32_t)SPG_MAXLEN) && st == FQ_OK) st = FQ_TOO_LONG;
+			if (lb > (uint32_t)A.stride || lq > (uint32_t)A.stride || lb >= (uint32_t)SPG_MAXLEN || lb != lq) len = 0; // keeps the kernels behind inside the rows
+			uint8_t* rb = A.rows[2 * f] + (size_t)p * A.stride;
+			uint8_t* rq = A.rows[2 * f + 1] + (size_t)p * A.stride;
+			for (uint32_t i = lane; i < len; i += 32)
+			{
+				rb[i] = t[b.s + i];
+				rq[i] = t[q.s + i];
+			}
+			if (lane == 0)
+			{
+				A.len[f][p] = (uint16_t)len;
+				FqRec r;
+				r.hs = hdr[f].s;
+				r.hl = hdr[f].e - hdr[f].s;
+				r.h2s = h2.s;
+				r.h2l = h2.e - h2.s;
+				A.rec[f][p] = r;
+			}
+		}
+		// headers must match up to the first space, "/1" and "/2" aside (AnalysisWorker.cpp:110-120)
+		{
+			const uint8_t* t1 = A.text[0];
+			const uint8_t* t2 = A.text[1];
+			uint32_t n1 = fq_token_len(t1, hdr[0], lane), n2 = fq_token_len(t2, hdr[1], lane);
+			if (n1 >= 2 && n2 >= 2 && t1[hdr[0].s + n1 - 2] == '/' && t1[hdr[0].s + n1 - 1] == '1' && t2[hdr[1].s + n2 - 2] == '/' && t2[hdr[1].s + n2 - 1] == '2')
+			{
+				n1 -= 2;
+				n2 -= 2;
+			}
+			bool diff = n1 != n2;
+			if (!diff)
+			{
+				for (uint32_t base = 0; base < n1 && !diff; base += 32)
+				{
+					const uint32_t i = base + (uint32_t)lane;
+					diff = __any_sync(0xffffffffu, i < n1 && t1[hdr[0].s + i] != t2[hdr[1].s + i]);
+				}
+			}
+			if (diff) st = FQ_HEADER_MISMATCH; // the first check of the worker: wins over the length checks
+		}
+		if (lane == 0)
+		{
+			A.fstat[p] = st;
+			if (st != FQ_OK) atomicMin(&A.plan->err_pair, (int)p);
+		}
+	}
+	max_len = __reduce_max_sync(0xffffffffu, max_len);
+	if (lane == 0 && max_len > 0) atomicMax(&A.plan->max_len, max_len);
+}
+
+// ---- output --------------------------------------------------------------------------------------------------------------------------------
+// bytes a pair contributes to the four streams
+__device__ __forceinline__ void fq_pair_sizes(const FqArgs& A, int p, uint32_t sz[4], int& l1, int& l2)
+{
+	const spg_result r = A.res[p];
+	l1 = r.len1;
+	l2 = r.len2;
+	const bool ok1 = l1 >= A.min_len, ok2 = l2 >= A.min_len;
+	const FqRec a = A.rec[0][p], b = A.rec[1][p];
+	const uint32_t s1 = a.hl + a.h2l + 2u * (uint32_t)l1 + 4u;
+	const uint32_t s2 = b.hl + b.h2l + 2u * (uint32_t)l2 + 4u;
+	sz[0] = sz[1] = sz[2] = sz[3] = 0;
+	if (ok1 && ok2)
+	{
+		sz[0] = s1;
+		sz[1] = s2;
+	}
+	else if (A.singles && ok1) sz[2] = s1;
+	else if (A.singles && ok2) sz[3] = s2;
+}
+
+// exclusive scan of four values per thread over a CTA of kFqOutPairs threads; returns the CTA totals in tot
+__device__ __forceinline__ void fq_block_scan4(uint32_t v[4], uint32_t tot[4])
+{
+	__shared__ uint32_t ws[4][kFqOutPairs / 32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inc[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	{
+		uint32_t x = v[k];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+			if (lane >= d) x += y;
+		}
+		inc[k] = x;
+		if (lane == 31) ws[k][warp] = x;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+	{
+		uint32_t before = 0, total = 0;
+		for (int w = 0; w < kFqOutPairs / 32; ++w)
+		{
+			const uint32_t s = ws[k][w];
+			if (w < warp) before += s;
+			total += s;
+		}
+		v[k] = before + inc[k] - v[k];
+		tot[k] = total;
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(kFqOutPairs) fq_out_sizes(const __grid_constant__ FqArgs A)
+{
+	const int n = A.plan->n_pairs;
+	const int first = blockIdx.x * kFqOutPairs;
+	if (first >= n) return;
+	const int p = first + (int)threadIdx.x;
+	uint32_t sz[4] = {0, 0, 0, 0}, tot[4];
+	int l1, l2;
+	if (p < n) fq_pair_sizes(A, p, sz, l1, l2);
+	fq_block_scan4(sz, tot);
+	if (threadIdx.x < 4) A.out_block[threadIdx.x][blockIdx.x] = tot[threadIdx.x];
+}
+
+// one CTA of 1024 threads: exclusive scan of the per-CTA byte counts of the four streams; totals into the plan
+__global__ void __launch_bounds__(1024) fq_out_scan(const __grid_constant__ FqArgs A)
+{
+	const int n = A.plan->n_pairs;
+	const int nb = (n + kFqOutPairs - 1) / kFqOutPairs;
+	const int k = threadIdx.x >> 8, t = threadIdx.x & 255; // 256 threads per stream
+	__shared__ uint32_t part[4][256];
+	// thread t of stream k owns the blocks [t*per, (t+1)*per)
+	const int per = (nb + 255) / 256;
+	uint32_t sum = 0;
+	for (int i = t * per; i < min(nb, (t + 1) * per); ++i) sum += A.out_block[k][i];
+	part[k][t] = sum;
+	__syncthreads();
+	if (t == 0)
+	{
+		uint32_t run = 0;
+		for (int i = 0; i < 256; ++i)
+		{
+			const uint32_t v = part[k][i];
+			part[k][i] = run;
+			run += v;
+		}
+		A.plan->out_bytes[k] = run;
+	}
+	__syncthreads();
+	uint32_t run = part[k][t];
+	for (int i = t * per; i < min(nb, (t + 1) * per); ++i)
+	{
+		const uint32_t v = A.out_block[k][i];
+		A.out_block[k][i] = run;
+		run += v;
+	}
+}
+
+// copies `n` bytes warp-cooperatively
+__device__ __forceinline__ void fq_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane)
+{
+	for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+// one record "header\nbases\nheader2\nquals\n" at dst
+__device__ __forceinline__ void fq_write_record(uint8_t* dst, const uint8_t* text, FqRec r, const uint8_t* bases, const uint8_t* quals, uint32_t len, int lane)
+{
+	fq_copy(dst, text + r.hs, r.hl, lane);
+	dst += r.hl;
+	fq_copy(dst + 1, bases, len, lane);
+	uint8_t* d2 = dst + 1 + len;
+	fq_copy(d2 + 1, text + r.h2s, r.h2l, lane);
+	uint8_t* d3 = d2 + 1 + r.h2l;
+	fq_copy(d3 + 1, quals, len, lane);
+	if (lane == 0)
+	{
+		dst[0] = '\n';
+		d2[0] = '\n';
+		d3[0] = '\n';
+		d3[1 + len] = '\n';
+	}
+}
+
+__device__ __forceinline__ int fq_base_index(uint8_t c) // Pileup::inc (src/cppNGS/Pileup.cpp:17-32); -1: ignored, -2: unknown
+{
+	switch (c)
+	{
+		case 'A': case 'a': return 0;
+		case 'C': case 'c': return 1;
+		case 'G': case 'g': return 2;
+		case 'T': case 't': return 3;
+		case 'N': case 'n': return 4;
+		case '-': case '~': return -1;
+		default: return -2;
+	}
+}
+
+__global__ void __launch_bounds__(kFqOutPairs) fq_out_write(const __grid_constant__ FqArgs A)
+{
+	const int n = A.plan->n_pairs;
+	const int first = blockIdx.x * kFqOutPairs;
+	if (first >= n) return;
+	__shared__ uint32_t offs[4][kFqOutPairs];
+	__shared__ unsigned int s_acons[2 * 40 * 5];
+	for (int i = threadIdx.x; i < 2 * 40 * 5; i += kFqOutPairs) s_acons[i] = 0;
+	{
+		const int p = first + (int)threadIdx.x;
+		uint32_t sz[4] = {0, 0, 0, 0}, tot[4];
+		int l1, l2;
+		if (p < n) fq_pair_sizes(A, p, sz, l1, l2);
+		fq_block_scan4(sz, tot);
+#pragma unroll
+		for (int k = 0; k < 4; ++k) offs[k][threadIdx.x] = A.out_block[k][blockIdx.x] + sz[k];
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int j = warp; j < kFqOutPairs; j += kFqOutPairs / 32)
+	{
+		const int p = first + j;
+		if (p >= n) break;
+		const spg_result r = A.res[p];
+		const int l1 = r.len1, l2 = r.len2;
+		const bool ok1 = l1 >= A.min_len, ok2 = l2 >= A.min_len;
+		const uint8_t* b1 = A.rows[0] + (size_t)p * A.stride;
+		const uint8_t* q1 = A.rows[1] + (size_t)p * A.stride;
+		const uint8_t* b2 = A.rows[2] + (size_t)p * A.stride;
+		const uint8_t* q2 = A.rows[3] + (size_t)p * A.stride;
+		if (ok1 && ok2)
+		{
+			fq_write_record(A.out[0] + offs[0][j], A.text[0], A.rec[0][p], b1, q1, (uint32_t)l1, lane);
+			fq_write_record(A.out[1] + offs[1][j], A.text[1], A.rec[1][p], b2, q2, (uint32_t)l2, lane);
+		}
+		else if (A.singles && ok1) fq_write_record(A.out[2] + offs[2][j], A.text[0], A.rec[0][p], b1, q1, (uint32_t)l1, lane);
+		else if (A.singles && ok2) fq_write_record(A.out[3] + offs[3][j], A.text[1], A.rec[1][p], b2, q2, (uint32_t)l2, lane);
+
+		// consensus of the adapter bases behind the insert, from the untrimmed reads (AnalysisWorker.cpp:279-290); -ec never edits them
+		if ((r.flags & SPG_F_INSERT) && r.status == 0)
+		{
+			const int o1 = A.len[0][p], o2 = A.len[1][p];
+			const int new_length = o2 - r.best_offset;
+			for (int i = lane; i < 80; i += 32)
+			{
+				const int rd = i / 40, k = i % 40;
+				int idx = -1;
+				if (rd == 0 && new_length + k < o1) idx = fq_base_index(b1[new_length + k]);
+				if (rd == 1 && k < r.best_offset && new_length + k < o2) idx = fq_base_index(b2[new_length + k]);
+				if (idx >= 0) atomicAdd(&s_acons[(rd * 40 + k) * 5 + idx], 1u);
+				else if (idx == -2) A.plan->acons_error = 1;
+			}
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < 2 * 40 * 5; i += kFqOutPairs)
+		if (s_acons[i]) atomicAdd(&A.acons[i], (unsigned long long)s_acons[i]);
+}
+
+} // namespace spg

@@ -44,6 +44,7 @@ struct KArgs
 	const uint16_t* len2;
 	spg_result* out;
 	long long n_pairs;
+	const int* n_dev; // if not null: the number of pairs is read from device memory (<= n_pairs, which then only sizes the grid)
 	int stride;     // bytes per row
 	int tile_pairs; // pairs per staged tile (multiple of 8)
 	int stages;
@@ -979,7 +980,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 	const int TP = A.tile_pairs;
 	const uint32_t plane_bytes = (uint32_t)TP * (uint32_t)A.stride;
 	const uint32_t stage_bytes = 4u * plane_bytes + 4u * (uint32_t)TP;
-	const long long n_tiles = (A.n_pairs + TP - 1) / TP;
+	const long long n_pairs = A.n_dev ? (long long)*A.n_dev : A.n_pairs;
+	const long long n_tiles = (n_pairs + TP - 1) / TP;
 	const uint32_t smem_base = smem_u32(smem);
 
 	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads) T.mmin[i] = A.mmin[i];
@@ -1019,7 +1021,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 					next_pair[s] = 0; // published to the consumers by the release of the arrive below
 				}
 				const long long first = t * TP;
-				const int cnt = (int)min((long long)TP, A.n_pairs - first);
+				const int cnt = (int)min((long long)TP, n_pairs - first);
 				// bulk copies move multiples of 16 bytes: a ragged last tile (cnt not a multiple of 8) reads up to 14 bytes past its
 				// last row, which stay inside the row planes (they are allocated in multiples of 8 rows)
 				const uint32_t row_bytes = ((uint32_t)cnt * (uint32_t)A.stride + 15u) & ~15u;
@@ -1046,7 +1048,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 			const uint32_t round = (uint32_t)(it / A.stages);
 			mbar_wait(&full_bar[s], round & 1u);
 			const long long first = t * TP;
-			const int cnt = (int)min((long long)TP, A.n_pairs - first);
+			const int cnt = (int)min((long long)TP, n_pairs - first);
 			const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 			const uint32_t lens = st + 4 * plane_bytes;
 			// lane 0 claims pairs from the tile's counter; the claim for the NEXT pair is issued before the current pair is processed, so

@@ -35,6 +35,7 @@ struct QcArgs
 	const uint16_t* len1;
 	const uint16_t* len2;
 	long long n_pairs;
+	const int* n_dev; // if not null: the number of pairs is read from device memory (<= n_pairs)
 	int stride;
 	int tile_pairs; // multiple of 8
 	int stages;     // <= kMaxStages
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 	const int TP = A.tile_pairs;
 	const uint32_t plane_bytes = (uint32_t)TP * (uint32_t)A.stride;
 	const uint32_t stage_bytes = 4u * plane_bytes + 4u * (uint32_t)TP;
-	const long long n_tiles = (A.n_pairs + TP - 1) / TP;
+	const long long n_pairs = A.n_dev ? (long long)*A.n_dev : A.n_pairs;
+	const long long n_tiles = (n_pairs + TP - 1) / TP;
 	const uint32_t smem_base = smem_u32(smem);
 
 	for (int i = threadIdx.x; i < 256; i += kThreads)
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 				const uint32_t round = (uint32_t)(it / A.stages);
 				if (round > 0) mbar_wait(&empty_bar[s], (round - 1) & 1u);
 				const long long first = t * TP;
-				const int cnt = (int)min((long long)TP, A.n_pairs - first);
+				const int cnt = (int)min((long long)TP, n_pairs - first);
 				const uint32_t row_bytes = ((uint32_t)cnt * (uint32_t)A.stride + 15u) & ~15u;
 				const uint32_t len_bytes = (uint32_t)((cnt + 7) / 8) * 16u;
 				const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
@@ -167,7 +169,7 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 			const uint32_t round = (uint32_t)(it / A.stages);
 			mbar_wait(&full_bar[s], round & 1u);
 			const long long first = t * TP;
-			const int cnt = (int)min((long long)TP, A.n_pairs - first);
+			const int cnt = (int)min((long long)TP, n_pairs - first);
 			const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 			const uint32_t lens = st + 4 * plane_bytes;
 			for (int pr = warp; pr < cnt; pr += CW)
@@ -251,7 +253,8 @@ __global__ void __launch_bounds__(256) qc_kernel_generic(const __grid_constant__
 	const int lane = threadIdx.x & 31;
 	const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-	for (long long r = gwarp; r < A.n_pairs; r += nwarps)
+	const long long n_pairs = A.n_dev ? (long long)*A.n_dev : A.n_pairs;
+	for (long long r = gwarp; r < n_pairs; r += nwarps)
 	{
 		for (int rd = 0; rd < 2; ++rd)
 		{

@@ -179,6 +179,36 @@ class Slot:
         self.len2 = _np_view(view.len2, (view.max_pairs,), np.uint16)
 
 
+class _FqConfig(C.Structure):
+    _fields_ = [("n_slots", C.c_int32), ("max_pairs", C.c_int32), ("max_len", C.c_int32), ("text_cap", C.c_int64), ("min_len", C.c_int32), ("singles", C.c_int32)]
+
+
+class _FqInput(C.Structure):
+    _fields_ = [("text1", C.c_void_p), ("text2", C.c_void_p), ("cap", C.c_int64)]
+
+
+class _FqOutput(C.Structure):
+    _fields_ = [("n_pairs", C.c_int32), ("records1", C.c_int32), ("records2", C.c_int32), ("consumed1", C.c_int64), ("consumed2", C.c_int64),
+                ("out", C.c_void_p * 4), ("out_bytes", C.c_int64 * 4), ("results", C.c_void_p), ("len1", C.c_void_p), ("len2", C.c_void_p),
+                ("frame_status", C.c_void_p), ("error_pair", C.c_int32), ("max_len", C.c_int32)]
+
+
+_lib.spg_fq_open.argtypes = [C.c_void_p, C.POINTER(_FqConfig), C.POINTER(C.c_void_p)]
+_lib.spg_fq_open.restype = C.c_int
+_lib.spg_fq_buffers.argtypes = [C.c_void_p, C.c_int, C.POINTER(_FqInput)]
+_lib.spg_fq_buffers.restype = C.c_int
+_lib.spg_fq_submit.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int]
+_lib.spg_fq_submit.restype = C.c_int
+_lib.spg_fq_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(_FqOutput)]
+_lib.spg_fq_wait.restype = C.c_int
+_lib.spg_fq_consensus_get.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+_lib.spg_fq_consensus_get.restype = C.c_int
+_lib.spg_fq_close.argtypes = [C.c_void_p]
+_lib.spg_fq_close.restype = None
+
+FQ_OK, FQ_HEADER_MISMATCH, FQ_LENGTH_MISMATCH, FQ_TOO_LONG = 0, 1, 2, 3
+
+
 class Engine:
     """One spg_ctx.  ``devices``: CUDA device ids; slot s runs on devices[s % len(devices)]."""
 
@@ -264,6 +294,64 @@ class Engine:
         if self._h:
             _lib.spg_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FastqChunk:
+    """What spg_fq_wait returns for one chunk (copies of the pinned buffers, so the slot can be reused)."""
+
+    def __init__(self, o):
+        n = o.n_pairs
+        self.n_pairs, self.records, self.consumed = n, (o.records1, o.records2), (o.consumed1, o.consumed2)
+        self.out = [C.string_at(o.out[k], o.out_bytes[k]) if o.out_bytes[k] else b"" for k in range(4)]
+        self.results = _np_view(o.results, (n,), RESULT_DTYPE).copy() if n else np.zeros(0, RESULT_DTYPE)
+        self.len1 = _np_view(o.len1, (n,), np.uint16).copy() if n else np.zeros(0, np.uint16)
+        self.len2 = _np_view(o.len2, (n,), np.uint16).copy() if n else np.zeros(0, np.uint16)
+        self.frame_status = _np_view(o.frame_status, (n,), np.uint8).copy() if n else np.zeros(0, np.uint8)
+        self.error_pair, self.max_len = o.error_pair, o.max_len
+
+
+class FastqStream:
+    """FASTQ text in, FASTQ text out on the device (spg_fq_*): framing, trimming, routing by min_len, record layout."""
+
+    def __init__(self, engine, n_slots=2, max_pairs=65536, max_len=160, text_cap=32 << 20, min_len=30, singles=False):
+        self.engine = engine
+        self._h = C.c_void_p()
+        cfg = _FqConfig(n_slots, max_pairs, max_len, text_cap, min_len, int(singles))
+        engine._check(_lib.spg_fq_open(engine._h, C.byref(cfg), C.byref(self._h)), "spg_fq_open")
+        self.text_cap, self.n_slots = text_cap, n_slots
+
+    def buffers(self, slot):
+        v = _FqInput()
+        self.engine._check(_lib.spg_fq_buffers(self._h, slot, C.byref(v)), "spg_fq_buffers")
+        return _np_view(v.text1, (v.cap,), np.uint8), _np_view(v.text2, (v.cap,), np.uint8)
+
+    def submit(self, slot, text1, text2, final1=True, final2=True):
+        b1, b2 = self.buffers(slot)
+        b1[: len(text1)] = np.frombuffer(text1, np.uint8)
+        b2[: len(text2)] = np.frombuffer(text2, np.uint8)
+        self.engine._check(_lib.spg_fq_submit(self._h, slot, len(text1), len(text2), int(final1), int(final2)), "spg_fq_submit")
+
+    def wait(self, slot):
+        o = _FqOutput()
+        self.engine._check(_lib.spg_fq_wait(self._h, slot, C.byref(o)), "spg_fq_wait")
+        return FastqChunk(o)
+
+    def consensus(self):
+        counts = np.zeros((2, 40, 5), np.int64)
+        unknown = C.c_int32(0)
+        self.engine._check(_lib.spg_fq_consensus_get(self._h, counts.ctypes.data, C.byref(unknown)), "spg_fq_consensus_get")
+        return counts, bool(unknown.value)
+
+    def close(self):
+        if self._h and self.engine._h:  # spg_destroy closes the streams that are still attached
+            _lib.spg_fq_close(self._h)
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:
