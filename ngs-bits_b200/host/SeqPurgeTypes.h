@@ -98,6 +98,7 @@ struct TrimmingParameters
 	int compression_level = 1; // Z_BEST_SPEED
 	std::string qc;
 	std::vector<int> gpus = {0}; // new, behaviour-neutral: CUDA devices the blocks are dealt to round robin
+	bool host_framing = false;   // new: FASTQ records are parsed/formatted on the host (block pipeline of the reference) instead of on the device
 };
 
 // counts of one pileup column, the part of cppNGS Pileup the consensus adapter needs (src/cppNGS/Pileup.cpp:17-32)

@@ -1,0 +1,469 @@
+// StreamPipeline.cpp -- the command line's default pipeline: the host only inflates and deflates, everything in between runs on the
+// GPUs: FASTQ text -> spg_fq_* (framing, rows, [-qc], trimming, routing, record layout, consensus) -> FASTQ text.
+//
+//   2 reader threads   one per input file list: gzread, cut after `block_size` records (4 lines each, counted with memchr), note the
+//                      longest sequence line -> queue of text chunks             (InputWorker::run, src/SeqPurge/InputWorker.cpp:16-77)
+//   this thread        pairs the chunks of the two lists, copies them into a pinned slot, spg_fq_submit; retires slots in order:
+//                      statistics from the 8-byte records, output text to the writers   (AnalysisWorker / OutputWorker seam)
+//   writers            one GzipTextWriter per output file (+ a shared deflate pool with -threads N > 1)
+#include "StreamPipeline.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+#include "GpuAnalysisWorker.h"
+#include "GzipTextWriter.h"
+#include "QcReport.h"
+
+namespace seqpurge
+{
+
+namespace
+{
+
+struct TextChunk
+{
+	std::vector<uint8_t> data;
+	int records = 0;      // entries readEntry would deliver for this text (an unterminated last line and an incomplete last record count)
+	int max_read_len = 0; // longest bases/qualities line (may include trailing '\r')
+	bool file_end = false;
+	size_t file_index = 0;
+};
+
+class ChunkQueue
+{
+public:
+	explicit ChunkQueue(size_t depth) : depth_(depth) {}
+	void push(std::unique_ptr<TextChunk> c)
+	{
+		std::unique_lock<std::mutex> l(mu_);
+		cv_.wait(l, [this] { return q_.size() < depth_ || aborted_; });
+		if (aborted_) return;
+		q_.push_back(std::move(c));
+		cv_.notify_all();
+	}
+	std::unique_ptr<TextChunk> pop() // nullptr: the reader is done (or failed: see failure())
+	{
+		std::unique_lock<std::mutex> l(mu_);
+		cv_.wait(l, [this] { return !q_.empty() || done_ || aborted_; });
+		if (q_.empty()) return nullptr;
+		std::unique_ptr<TextChunk> c = std::move(q_.front());
+		q_.pop_front();
+		cv_.notify_all();
+		return c;
+	}
+	void finish(std::exception_ptr e)
+	{
+		std::lock_guard<std::mutex> g(mu_);
+		done_ = true;
+		failure_ = e;
+		cv_.notify_all();
+	}
+	void abort()
+	{
+		std::lock_guard<std::mutex> g(mu_);
+		aborted_ = true;
+		cv_.notify_all();
+	}
+	std::exception_ptr failure()
+	{
+		std::lock_guard<std::mutex> g(mu_);
+		return failure_;
+	}
+
+private:
+	size_t depth_;
+	std::mutex mu_;
+	std::condition_variable cv_;
+	std::deque<std::unique_ptr<TextChunk>> q_;
+	bool done_ = false, aborted_ = false;
+	std::exception_ptr failure_;
+};
+
+// reads the files of one list, cuts the inflated text after every `pairs` records
+void readerLoop(const std::vector<std::string>& files, int pairs, ChunkQueue& out)
+{
+	try
+	{
+		std::vector<uint8_t> buf((size_t)4 << 20);
+		for (size_t fi = 0; fi < files.size(); ++fi)
+		{
+			gzFile gz = gzopen(files[fi].c_str(), "rb");
+			if (!gz) throw FileAccessException("Could not open file '" + files[fi] + "' for reading!");
+			gzbuffer(gz, 1 << 20);
+			std::unique_ptr<TextChunk> cur(new TextChunk());
+			cur->file_index = fi;
+			long long lines = 0;   // complete lines in cur
+			size_t line_len = 0;   // bytes of the current (incomplete) line
+			const long long cut = 4ll * pairs;
+			for (;;)
+			{
+				const int n = gzread(gz, buf.data(), (unsigned)buf.size());
+				if (n < 0)
+				{
+					int err = Z_OK;
+					const char* msg = gzerror(gz, &err);
+					const std::string m = msg ? msg : "";
+					gzclose(gz);
+					throw FileParseException("Error while reading file '" + files[fi] + "': " + m);
+				}
+				if (n == 0) break;
+				const uint8_t* p = buf.data();
+				const uint8_t* end = p + n;
+				const uint8_t* start = p; // first byte not yet appended to cur
+				while (p < end)
+				{
+					const uint8_t* nl = (const uint8_t*)memchr(p, '\n', (size_t)(end - p));
+					if (!nl)
+					{
+						line_len += (size_t)(end - p);
+						break;
+					}
+					line_len += (size_t)(nl - p);
+					if (lines & 1) cur->max_read_len = (int)std::min<size_t>(std::max<size_t>((size_t)cur->max_read_len, line_len), 1u << 30);
+					line_len = 0;
+					++lines;
+					p = nl + 1;
+					if (lines == cut)
+					{
+						cur->data.insert(cur->data.end(), start, p);
+						cur->records = pairs;
+						out.push(std::move(cur));
+						cur.reset(new TextChunk());
+						cur->file_index = fi;
+						lines = 0;
+						start = p;
+					}
+				}
+				cur->data.insert(cur->data.end(), start, end);
+			}
+			gzclose(gz);
+			if (line_len > 0) // unterminated last line
+			{
+				if (lines & 1) cur->max_read_len = (int)std::min<size_t>(std::max<size_t>((size_t)cur->max_read_len, line_len), 1u << 30);
+				++lines;
+			}
+			cur->records = (int)((lines + 3) / 4);
+			cur->file_end = true;
+			out.push(std::move(cur));
+		}
+		out.finish(nullptr);
+	}
+	catch (...)
+	{
+		out.finish(std::current_exception());
+	}
+}
+
+// the `index`-th record of a chunk as the reference's reader delivers it (error reporting only)
+FastqEntry entryAt(const TextChunk& c, int index)
+{
+	FastqEntry e;
+	const uint8_t* p = c.data.data();
+	const uint8_t* end = p + c.data.size();
+	std::string* field[4] = {&e.header, &e.bases, &e.header2, &e.qualities};
+	long long line = 0;
+	while (p < end && line < 4ll * index + 4)
+	{
+		const uint8_t* nl = (const uint8_t*)memchr(p, '\n', (size_t)(end - p));
+		const uint8_t* le = nl ? nl : end;
+		if (line >= 4ll * index)
+		{
+			const uint8_t* e2 = le;
+			while (e2 > p && e2[-1] == '\r') --e2;
+			field[line - 4ll * index]->assign((const char*)p, (size_t)(e2 - p));
+		}
+		++line;
+		p = nl ? nl + 1 : end;
+	}
+	return e;
+}
+
+bool endsWith(const std::string& s, const char* suffix)
+{
+	const size_t n = strlen(suffix);
+	return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+bool isAcgtn(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T' || c == 'N'; }
+[[noreturn]] void throwBadComplement(const std::string& bases)
+{
+	for (char c : bases)
+		if (!isAcgtn(c)) throw ProgrammingException(std::string("Could not convert base '") + c + "' to complement!"); // Sequence.cpp:68
+	throw ProgrammingException("Could not convert base to complement!");
+}
+
+// the exception the reference's worker raises for this pair (same checks, same order as GpuAnalysisWorker::start / wait)
+[[noreturn]] void throwPairError(const FastqEntry& e1, const FastqEntry& e2, int frame_status, int result_status)
+{
+	auto token = [](const std::string& h) {
+		const size_t p = h.find(' ');
+		return p == std::string::npos ? h : h.substr(0, p);
+	};
+	std::string t1 = token(e1.header), t2 = token(e2.header);
+	if (endsWith(t1, "/1") && endsWith(t2, "/2"))
+	{
+		t1.resize(t1.size() - 2);
+		t2.resize(t2.size() - 2);
+	}
+	if (t1 != t2) throw ArgumentException("Headers of reads do not match:\n" + t1 + "\n" + t2);
+	if (e1.qualities.size() != e1.bases.size() || e2.qualities.size() != e2.bases.size())
+		throw FileParseException("Differing length of bases and qualities string in sequence '" + e1.header + "'.");
+	if (!std::all_of(e2.bases.begin(), e2.bases.end(), isAcgtn)) throwBadComplement(e2.bases);
+	if (std::max(e1.bases.size(), e2.bases.size()) >= (size_t)MAXLEN)
+		throw ArgumentException("Read length unsupported! A maximum read length of " + std::to_string(MAXLEN) + " is supported!");
+	if (result_status == SPG_PAIR_BAD_BASE_EC) throwBadComplement(e1.bases);
+	throw ProgrammingException("pair rejected by the device (frame status " + std::to_string(frame_status) + ", result status " + std::to_string(result_status) + ")");
+}
+
+} // namespace
+
+void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, TrimmingStatistics& stats, ErrorCorrectionStatistics& ec_stats, spg_qc_stats* qc_stats)
+{
+	const int pairs = params.block_size;
+	const bool singles = !params.out3.empty();
+	// SPG_TIMING=1: where this thread spent its time (stderr)
+	const bool timing = getenv("SPG_TIMING") != nullptr;
+	using clk = std::chrono::steady_clock;
+	double t_init = 0, t_pop = 0, t_copy = 0, t_wait = 0, t_stats = 0, t_write = 0, t_close = 0;
+	auto since = [](clk::time_point t0) { return std::chrono::duration<double>(clk::now() - t0).count(); };
+	clk::time_point tp = clk::now();
+	const int n_slots = std::max(2, std::min(params.block_prefetch, 4)) * (int)params.gpus.size(); // chunks in flight: the GPU part of a chunk is far shorter than its inflate
+	(void)summary;
+
+	spg_params ep = toEngineParams(params);
+	spg_ctx* engine = nullptr;
+	if (spg_create(&engine, &ep, params.gpus.data(), (int)params.gpus.size(), 0, 0, 0) != SPG_OK)
+		throw Exception(std::string("Could not initialize the CUDA trimming engine: ") + spg_last_error(nullptr));
+	struct EngineGuard
+	{
+		spg_ctx* e;
+		~EngineGuard() { spg_destroy(e); }
+	} engine_guard{engine};
+
+	t_init += since(tp);
+
+	std::unique_ptr<WorkerPool> pool;
+	if (params.threads > 1) pool.reset(new WorkerPool(params.threads));
+	std::unique_ptr<GzipTextWriter> writers[4];
+	writers[0].reset(new GzipTextWriter(params.out1, params.compression_level, pool.get()));
+	writers[1].reset(new GzipTextWriter(params.out2, params.compression_level, pool.get()));
+	if (singles)
+	{
+		writers[2].reset(new GzipTextWriter(params.out3 + "_R1.fastq.gz", params.compression_level, pool.get()));
+		writers[3].reset(new GzipTextWriter(params.out3 + "_R2.fastq.gz", params.compression_level, pool.get()));
+	}
+
+	ChunkQueue q1(4), q2(4);
+	std::thread reader1([&]() { readerLoop(params.files_in1, pairs, q1); });
+	std::thread reader2([&]() { readerLoop(params.files_in2, pairs, q2); });
+	struct ReaderGuard
+	{
+		ChunkQueue &a, &b;
+		std::thread &t1, &t2;
+		~ReaderGuard()
+		{
+			a.abort();
+			b.abort();
+			if (t1.joinable()) t1.join();
+			if (t2.joinable()) t2.join();
+		}
+	} reader_guard{q1, q2, reader1, reader2};
+
+	spg_fq* fq = nullptr;
+	int fq_max_len = 0;
+	int64_t fq_text_cap = 0;
+	int64_t acons[2][40][5];
+	memset(acons, 0, sizeof(acons));
+	bool acons_unknown = false;
+	auto closeStream = [&]() {
+		if (!fq) return;
+		int64_t c[2][40][5];
+		int32_t unknown = 0;
+		if (spg_fq_consensus_get(fq, c, &unknown) != SPG_OK) throw Exception(spg_last_error(engine));
+		for (int k = 0; k < 2 * 40 * 5; ++k) (&acons[0][0][0])[k] += (&c[0][0][0])[k];
+		if (unknown) acons_unknown = true;
+		spg_fq_close(fq);
+		fq = nullptr;
+	};
+
+	struct InFlight
+	{
+		int slot;
+		std::unique_ptr<TextChunk> a, b;
+	};
+	std::deque<InFlight> in_flight;
+	int next_slot = 0;
+
+	auto retire = [&]() {
+		InFlight f = std::move(in_flight.front());
+		in_flight.pop_front();
+		spg_fq_output o;
+		clk::time_point t0 = clk::now();
+		if (spg_fq_wait(fq, f.slot, &o) != SPG_OK) throw Exception(spg_last_error(engine));
+		t_wait += since(t0);
+		t0 = clk::now();
+		if (o.error_pair >= 0)
+		{
+			const int p = o.error_pair;
+			throwPairError(entryAt(*f.a, p), entryAt(*f.b, p), o.frame_status[p], o.results[p].status);
+		}
+		if (o.n_pairs != f.a->records || (size_t)o.consumed1 != f.a->data.size() || (size_t)o.consumed2 != f.b->data.size())
+			throw ProgrammingException("the device framed the chunk differently from the reader");
+		// statistics (OutputWorker.cpp:36-77) from the result records
+		const int min_len = std::max(params.min_len, 0);
+		long long removed = 0, t_insert = 0, t_adapter = 0, t_q = 0, t_n = 0;
+		for (int r = 0; r < o.n_pairs; ++r)
+		{
+			const spg_result& k = o.results[r];
+			if (k.flags & SPG_F_INSERT) t_insert += 2;
+			if (k.flags & SPG_F_ADAPTER) t_adapter += 2;
+			t_q += ((k.flags & SPG_F_Q1) ? 1 : 0) + ((k.flags & SPG_F_Q2) ? 1 : 0);
+			t_n += ((k.flags & SPG_F_N1) ? 1 : 0) + ((k.flags & SPG_F_N2) ? 1 : 0);
+			const bool ok1 = (int)k.len1 >= min_len, ok2 = (int)k.len2 >= min_len;
+			if (ok1 && ok2) {}
+			else if (singles && ok1) removed += 1;
+			else if (singles && ok2) removed += 1;
+			else removed += 2;
+			stats.bases_remaining[k.len1] += 1;
+			stats.bases_remaining[k.len2] += 1;
+			const int o1 = o.len1[r], o2 = o.len2[r];
+			if (o1 > 0) stats.bases_perc_trim_sum += (double)(o1 - (int)k.len1) / o1;
+			if (o2 > 0) stats.bases_perc_trim_sum += (double)(o2 - (int)k.len2) / o2;
+		}
+		stats.read_num += 2LL * o.n_pairs;
+		stats.reads_trimmed_insert += (double)t_insert;
+		stats.reads_trimmed_adapter += (double)t_adapter;
+		stats.reads_trimmed_q += (double)t_q;
+		stats.reads_trimmed_n += (double)t_n;
+		stats.reads_removed += (double)removed;
+		t_stats += since(t0);
+		t0 = clk::now();
+		for (int k = 0; k < 4; ++k)
+			if (writers[k] && o.out_bytes[k] > 0) writers[k]->write(std::vector<uint8_t>(o.out[k], o.out[k] + o.out_bytes[k]));
+		t_write += since(t0);
+	};
+
+	auto moreEntries = [&](size_t fi, bool first_has_more) {
+		const std::string& a = params.files_in1[std::min(fi, params.files_in1.size() - 1)];
+		const std::string& b = params.files_in2[std::min(fi, params.files_in2.size() - 1)];
+		// InputWorker.cpp:37-44
+		if (first_has_more) throw FileParseException("File " + a + " has more entries than " + b + "!");
+		throw FileParseException("File " + b + " has more entries than " + a + "!");
+	};
+
+	for (;;)
+	{
+		clk::time_point t0 = clk::now();
+		std::unique_ptr<TextChunk> a = q1.pop(), b = q2.pop();
+		t_pop += since(t0);
+		if (!a || !b)
+		{
+			if (q1.failure()) std::rethrow_exception(q1.failure());
+			if (q2.failure()) std::rethrow_exception(q2.failure());
+			if (a || b) throw ProgrammingException("input file lists ended at different chunks");
+			break;
+		}
+		if (a->file_index != b->file_index) throw ProgrammingException("readers out of step");
+		if (a->records != b->records)
+		{
+			while (!in_flight.empty()) retire(); // the pairs in front of the mismatch are processed like in the reference
+			moreEntries(a->file_index, a->records > b->records);
+		}
+		// one file ended on this chunk, the other did not: whatever follows in the other file is a surplus entry
+		while (a->file_end != b->file_end)
+		{
+			std::unique_ptr<TextChunk>& open = a->file_end ? b : a;
+			ChunkQueue& q = a->file_end ? q2 : q1;
+			std::unique_ptr<TextChunk> nxt = q.pop();
+			if (!nxt) throw ProgrammingException("reader ended inside a file");
+			if (nxt->records > 0)
+			{
+				while (!in_flight.empty()) retire();
+				moreEntries(a->file_index, !a->file_end);
+			}
+			open->file_end = nxt->file_end;
+		}
+		if (a->records == 0) continue;
+
+		const int need_len = std::min(std::max(a->max_read_len, b->max_read_len), MAXLEN - 1);
+		const int64_t need_text = (int64_t)std::max(a->data.size(), b->data.size());
+		if (!fq || need_len > fq_max_len || need_text > fq_text_cap)
+		{
+			while (!in_flight.empty()) retire();
+			closeStream();
+			spg_fq_config cfg;
+			cfg.n_slots = n_slots;
+			cfg.max_pairs = pairs;
+			cfg.max_len = std::min(MAXLEN - 1, std::max(std::max((need_len + 15) / 16 * 16, fq_max_len), 160));
+			cfg.text_cap = std::max<int64_t>(std::max<int64_t>(need_text + need_text / 4, fq_text_cap), 1 << 20);
+			cfg.min_len = std::max(params.min_len, 0);
+			cfg.singles = singles ? 1 : 0;
+			t0 = clk::now();
+			if (spg_fq_open(engine, &cfg, &fq) != SPG_OK) throw Exception(std::string("Could not open the FASTQ stream on the device: ") + spg_last_error(engine));
+			t_init += since(t0);
+			fq_max_len = cfg.max_len;
+			fq_text_cap = cfg.text_cap;
+			next_slot = 0;
+		}
+		if ((int)in_flight.size() == n_slots) retire();
+		const int slot = next_slot;
+		next_slot = (next_slot + 1) % n_slots;
+		spg_fq_input in;
+		if (spg_fq_buffers(fq, slot, &in) != SPG_OK) throw Exception(spg_last_error(engine));
+		t0 = clk::now();
+		memcpy(in.text1, a->data.data(), a->data.size());
+		memcpy(in.text2, b->data.data(), b->data.size());
+		t_copy += since(t0);
+		if (spg_fq_submit(fq, slot, (int64_t)a->data.size(), (int64_t)b->data.size(), 1, 1) != SPG_OK) throw Exception(spg_last_error(engine));
+		in_flight.push_back(InFlight{slot, std::move(a), std::move(b)});
+	}
+	while (!in_flight.empty()) retire();
+	closeStream();
+	if (acons_unknown) throw ArgumentException("Unknown base in the adapter consensus window!"); // Pileup::inc
+	for (int i = 0; i < 40; ++i)
+	{
+		BaseCounts* dst[2] = {&stats.acons1[(size_t)i], &stats.acons2[(size_t)i]};
+		for (int rd = 0; rd < 2; ++rd)
+		{
+			dst[rd]->a += acons[rd][i][0];
+			dst[rd]->c += acons[rd][i][1];
+			dst[rd]->g += acons[rd][i][2];
+			dst[rd]->t += acons[rd][i][3];
+			dst[rd]->n += acons[rd][i][4];
+		}
+	}
+	if (params.ec)
+	{
+		spg_ec_stats s;
+		if (spg_ec_stats_get(engine, &s) != SPG_OK) throw Exception(spg_last_error(engine));
+		for (int i = 0; i < MAXLEN; ++i)
+		{
+			ec_stats.mismatch_r1[(size_t)i] += s.mismatch_r1[i];
+			ec_stats.mismatch_r2[(size_t)i] += s.mismatch_r2[i];
+			ec_stats.errors_per_read[(size_t)i] += s.errors_per_read[i];
+		}
+	}
+	if (qc_stats && !params.qc.empty())
+	{
+		if (spg_qc_stats_get(engine, qc_stats) != SPG_OK) throw Exception(spg_last_error(engine));
+	}
+	tp = clk::now();
+	for (int k = 0; k < 4; ++k)
+		if (writers[k]) writers[k]->close();
+	t_close += since(tp);
+	if (timing)
+		fprintf(stderr, "[spg timing] init %.3f s, waiting for input %.3f s, copy to pinned %.3f s, waiting for the GPU %.3f s, statistics %.3f s, handing to writers %.3f s, closing writers %.3f s\n",
+		        t_init, t_pop, t_copy, t_wait, t_stats, t_write, t_close);
+}
+
+} // namespace seqpurge

@@ -1,10 +1,15 @@
-// seqpurge_b200 -- command line with the flags of the reference's SeqPurge (src/SeqPurge/main.cpp:17-54, doc/tools/SeqPurge.md),
-// the reference's block pipeline (load -> analyze -> write, src/SeqPurge/ThreadCoordinator.cpp:83-106) and the reference's output
-// routing and statistics (src/SeqPurge/OutputWorker.cpp:36-77, src/SeqPurge/FastqWriter.cpp:17-38) -- with the analysis step
-// handed to the CUDA engine through GpuAnalysisWorker instead of AnalysisWorker + QThreadPool.
+// seqpurge_b200 -- command line with the flags of the reference's SeqPurge (src/SeqPurge/main.cpp:17-54, doc/tools/SeqPurge.md).
 //
-// Jobs are dealt to the GPUs round robin (slot s -> device s % n) and retired in submission order, so the output equals the
-// reference's `-threads 1` output whatever the number of GPUs. -qc writes the read statistics as qcML (values only, no plots). Not supported here: -debug, -progress.
+// Default pipeline (StreamPipeline.cpp): the host inflates the inputs and deflates the outputs; FASTQ framing, trimming, routing by
+// -min_len, record layout, adapter consensus and -qc statistics run on the GPUs behind spg_fq_* of the C ABI.
+// -host_framing selects the reference's block pipeline instead (load -> analyze -> write, src/SeqPurge/ThreadCoordinator.cpp:83-106;
+// output routing and statistics of src/SeqPurge/OutputWorker.cpp:36-77, src/SeqPurge/FastqWriter.cpp:17-38) with records parsed and
+// formatted on the host and only the analysis step handed to the CUDA engine through GpuAnalysisWorker -- the binding INTEGRATION.md
+// describes for the reference itself.
+//
+// Blocks are dealt to the GPUs round robin (slot s -> device s % n) and retired in submission order, so the output equals the
+// reference's `-threads 1` output whatever the number of GPUs. -threads N (N > 1) deflates the output with N threads (same content,
+// other .gz bytes). -qc writes the read statistics as qcML (values only, no plots). Not supported here: -debug, -progress.
 #include <chrono>
 #include <condition_variable>
 #include <exception>
@@ -23,6 +28,7 @@
 #include "FastqFileStream.h"
 #include "GpuAnalysisWorker.h"
 #include "QcReport.h"
+#include "StreamPipeline.h"
 
 using namespace seqpurge;
 
@@ -142,7 +148,9 @@ void usage()
 	             "Mandatory: -in1 <files> -in2 <files> -out1 <file> -out2 <file>\n"
 	             "Optional (defaults of SeqPurge): -a1 -a2 -match_perc 80 -mep 0.000001 -qcut 15 -qwin 5 -qoff 33 -ncut 7 -min_len 30 -threads 1\n"
 	             "          -out3 <prefix> -summary <file> -qc <file.qcML> -block_size 10000 -block_prefetch 32 -ec -compression_level 1\n"
-	             "New: -gpus 0[,1,...]  CUDA devices the blocks are dealt to (default 0)\n";
+	             "New: -gpus 0[,1,...]  CUDA devices the blocks are dealt to (default 0)\n"
+	             "     -threads N       N > 1: the output files are deflated by N threads (same content, different .gz bytes)\n"
+	             "     -host_framing    parse and format FASTQ records on the host (the reference's block pipeline) instead of on the device\n";
 }
 
 } // namespace
@@ -190,6 +198,7 @@ int main(int argc, char** argv)
 			else if (f == "-ec") params.ec = true;
 			else if (f == "-gpus") params.gpus = parseIntList(next());
 			else if (f == "-qc") params.qc = next();
+			else if (f == "-host_framing") params.host_framing = true;
 			else if (f == "-debug") throw CommandLineParsingException("Parameter '" + f + "' is not supported by seqpurge_b200.");
 			else throw CommandLineParsingException("Unknown parameter '" + f + "'!");
 		}
@@ -202,6 +211,34 @@ int main(int argc, char** argv)
 		if (params.block_size < 1 || params.block_prefetch < 1 || params.gpus.empty()) throw CommandLineParsingException("block_size, block_prefetch and gpus must be positive!");
 
 		const auto t_start = std::chrono::steady_clock::now();
+		if (!params.host_framing) // default: FASTQ framing and output assembly on the device (StreamPipeline.cpp)
+		{
+			std::ofstream summary_file;
+			if (!params.summary.empty())
+			{
+				summary_file.open(params.summary);
+				if (!summary_file) throw FileAccessException("Could not open file '" + params.summary + "' for writing!");
+			}
+			std::ostream& summary = params.summary.empty() ? std::cout : summary_file;
+			TrimmingStatistics stats;
+			ErrorCorrectionStatistics ec_stats;
+			std::unique_ptr<spg_qc_stats> qc_stats(new spg_qc_stats());
+			memset(qc_stats.get(), 0, sizeof(spg_qc_stats));
+			runStreamPipeline(params, summary, stats, ec_stats, qc_stats.get());
+			stats.writeStatistics(summary, params);
+			if (!params.qc.empty())
+			{
+				std::vector<std::string> sources = params.files_in1;
+				sources.insert(sources.end(), params.files_in2.begin(), params.files_in2.end());
+				storeQcML(params.qc, *qc_stats, sources, "");
+			}
+			if (params.ec) ec_stats.writeStatistics(summary);
+			const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+			char buf[64];
+			snprintf(buf, sizeof(buf), "%.3fs", secs);
+			summary << "overall runtime: " << buf << "\n";
+			return 0;
+		}
 		InputStreams in;
 		in.istream1.reset(new FastqFileStream(params.files_in1[0]));
 		in.istream2.reset(new FastqFileStream(params.files_in2[0]));

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """End-to-end command-line comparison (the X boundary of SURVEY.md 8d: gz in -> trim -> gz out, informational):
 seqpurge_b200 (CUDA engine) vs the CPU oracle CLI with all host threads, same synthetic FASTQ.gz input, outputs compared byte for byte.
-usage: python profiles/cli_throughput.py [pairs]"""
+usage: python profiles/cli_throughput.py [pairs] [copies]   (the generated files are concatenated `copies` times: multi-member gzip)"""
 import os
 import subprocess
 import sys
@@ -36,17 +36,42 @@ for r, (bk, qk) in enumerate((("bases1", "quals1"), ("bases2", "quals2")), start
         p.stdin.write(B[i].tobytes() + b"\n+\n" + Q[i].tobytes() + b"\n")
     p.stdin.close()
     p.wait()
+copies = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+if copies > 1:
+    for r in (1, 2):
+        subprocess.run("cat " + " ".join([f"{d}/in{r}.fastq.gz"] * copies) + f" > {d}/inx{r}.fastq.gz && mv {d}/inx{r}.fastq.gz {d}/in{r}.fastq.gz", shell=True, check=True)
+    n *= copies
+os.environ["SPG_TIMING"] = "1"
 threads = len(os.sched_getaffinity(0))
+try:  # the cgroup limit is what the box really gives
+    quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+    if quota != "max":
+        threads = max(1, min(threads, int(int(quota) / int(period))))
+except OSError:
+    pass
+cli = os.path.join(ROOT, "ngs-bits_b200", "bin", "seqpurge_b200")
+plain = {}
+for r in (1, 2):  # uncompressed copies of the inputs: the inflate-free upper bound of the pipeline
+    plain[r] = f"{d}/in{r}.fastq"
+    subprocess.run(f"gzip -dc {d}/in{r}.fastq.gz > {plain[r]}", shell=True, check=True)
 runs = {
-    "oracle_cli": [os.path.join(ROOT, "oracle", "build", "seqpurge_oracle"), "-threads", str(threads)],
-    "seqpurge_b200": [os.path.join(ROOT, "ngs-bits_b200", "bin", "seqpurge_b200")],
+    "oracle_cli": ([os.path.join(ROOT, "oracle", "build", "seqpurge_oracle"), "-threads", str(threads)], "gz"),
+    "b200_host_framing": ([cli, "-host_framing"], "gz"),
+    "seqpurge_b200": ([cli], "gz"),
+    f"b200_deflate_threads_{threads}": ([cli, "-threads", str(threads), "-block_size", "32768"], "gz"),
+    f"b200_plain_in_deflate_threads_{threads}": ([cli, "-threads", str(threads), "-block_size", "32768"], "plain"),
+    f"b200_plain_in_level0_out_threads_{threads}": ([cli, "-threads", str(threads), "-block_size", "32768", "-compression_level", "0"], "plain"),
 }
-for name, cmd in runs.items():
+for name, (cmd, kind) in runs.items():
     os.makedirs(f"{d}/{name}")
+    in1, in2 = (f"{d}/in1.fastq.gz", f"{d}/in2.fastq.gz") if kind == "gz" else (plain[1], plain[2])
     t0 = time.perf_counter()
-    subprocess.run(cmd + ["-in1", f"{d}/in1.fastq.gz", "-in2", f"{d}/in2.fastq.gz", "-out1", f"{d}/{name}/o1.fastq.gz", "-out2", f"{d}/{name}/o2.fastq.gz",
-                          "-summary", f"{d}/{name}/s.txt"], check=True)
+    subprocess.run(cmd + ["-in1", in1, "-in2", in2, "-out1", f"{d}/{name}/o1.fastq.gz", "-out2", f"{d}/{name}/o2.fastq.gz", "-summary", f"{d}/{name}/s.txt"], check=True)
     el = time.perf_counter() - t0
-    print(f"{name}: {el:.2f} s for {n} pairs = {n / el / 1e6:.3f} Mpairs/s end to end (gz in, gz out)")
-same = all(open(f"{d}/oracle_cli/{f}", "rb").read() == open(f"{d}/seqpurge_b200/{f}", "rb").read() for f in ("o1.fastq.gz", "o2.fastq.gz"))
-print("outputs byte-identical:", same)
+    print(f"{name}: {el:.2f} s for {n} pairs = {n / el / 1e6:.3f} Mpairs/s end to end ({kind} in, gz out)", flush=True)
+for name in runs:
+    if name == "oracle_cli":
+        continue
+    same = all(open(f"{d}/oracle_cli/{f}", "rb").read() == open(f"{d}/{name}/{f}", "rb").read() for f in ("o1.fastq.gz", "o2.fastq.gz"))
+    content = all(subprocess.run(f"bash -c 'cmp <(gzip -dc {d}/oracle_cli/{f}) <(gzip -dc {d}/{name}/{f})'", shell=True).returncode == 0 for f in ("o1.fastq.gz", "o2.fastq.gz"))
+    print(f"{name}: .gz bytes identical to the oracle: {same}; decompressed content identical: {content}")
