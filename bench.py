@@ -327,7 +327,7 @@ def main():
                    "l2": "inputs larger than L2 (each step reads a distinct 6.0 GB batch at the default size)", "parallelism": f"replicated engine x{world}, stream sharded by rank, no collective",
                    "insert_hit_fraction": frac_insert},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_pair": B_ALG, "kernel_ms_mean": mean_kernel_ms, "kernel": "spg::trim_kernel<NW=5,CW=8,MINB=3>",
+                     "algorithmic_bytes_per_pair": B_ALG, "kernel_ms_mean": mean_kernel_ms, "kernel": "spg::trim_kernel<NW=5,CW=8,MINB=3,FULL=150>",
                      "note": "the offset sweep is integer-issue bound, not HBM bound (DESIGN.md)"},
         "clocks": clocks, "gpu_launches": launches,
     }

@@ -227,6 +227,7 @@ void spg_fq_close(spg_fq* fq);
 #define SPG_OPT_MIN_BLOCKS 3      /* kernel variant compiled for at least 2, 3 or 4 resident CTAs per SM (register budget) */
 #define SPG_OPT_TILE_PAIRS 4      /* pairs per TMA-staged tile (multiple of 8; 0 = automatic) */
 #define SPG_OPT_STAGES 5          /* depth of the TMA ring, 2..4 (0 = automatic) */
+#define SPG_OPT_FULL_LEN 6        /* read length the kernel variant is chosen for (fast path for full-length pairs): -1 = automatic, 0 = general kernel only */
 int spg_set_option(spg_ctx* ctx, int option, int value);
 
 /* number of kernel launches issued by this context so far (bench.py reports it as gpu_launches) */

@@ -209,6 +209,7 @@ struct Device
 	unsigned long long* d_ec = nullptr; // 3 * SPG_MAXLEN
 	unsigned long long* d_qc = nullptr; // spg::kQcWords accumulators of the -qc statistics
 	int occ[4][3] = {};                 // resident CTAs per SM for NW = 0,5,8,10 x kernel variant (min blocks 2,3,4)
+	int full_occ[4][5] = {};            // same for the variants compiled for one read length (full_index)
 	int qc_occ[3] = {};                 // same for qc_kernel, NW = 5,8,10
 };
 
@@ -254,6 +255,7 @@ struct spg_ctx
 	int force_bytewise = 0;
 	int ctas_per_sm = 0; // 0 = occupancy
 	int min_blocks = 3; // __launch_bounds__ min CTAs/SM of the kernel variant (register budget)
+	int full_len = -1;  // SPG_OPT_FULL_LEN: -1 = automatic (max_len of the context / longest line of the previous chunk), 0 = general kernel
 	int tile_pairs = 0; // 0 = automatic
 	int stages = 0;     // 0 = automatic
 	long long launches = 0;
@@ -295,22 +297,22 @@ void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 
 constexpr int kCW = 8; // consumer warps per CTA (+1 producer warp); geometry sweeps showed 4/6/8 within 3%
 
-template <int NW, int MINB>
+template <int NW, int MINB, int FULL = 0>
 cudaError_t launch_cfg(const spg::KArgs& a, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, int* occ_cache)
 {
 	// per (device, instantiation): raise the dynamic shared memory limit once, ask the occupancy calculator once
 	if (*occ_cache == 0)
 	{
-		cudaError_t e = cudaFuncSetAttribute(spg::trim_kernel<NW, kCW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaFuncSetAttribute(spg::trim_kernel<NW, kCW, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return e;
 		int n = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::trim_kernel<NW, kCW, MINB>, (kCW + 1) * 32, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::trim_kernel<NW, kCW, MINB, FULL>, (kCW + 1) * 32, smem);
 		if (e != cudaSuccess) return e;
 		*occ_cache = n < 1 ? 1 : n;
 	}
 	const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, *occ_cache) : *occ_cache;
 	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * per_sm);
-	spg::trim_kernel<NW, kCW, MINB><<<grid, (kCW + 1) * 32, smem, stream>>>(a);
+	spg::trim_kernel<NW, kCW, MINB, FULL><<<grid, (kCW + 1) * 32, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 
@@ -325,11 +327,24 @@ cudaError_t launch_nw(const spg::KArgs& a, int minb, int sm_count, int ctas_per_
 	}
 }
 
-// n_dev: optional device pointer to the actual pair count (<= n); n then sizes the grid only
+// Kernel variants compiled for one read length (fast path for pairs of two full-length reads, spg_kernel.cuh): the usual
+// lengths of Illumina runs. Any other length runs the general kernel; results do not depend on the choice.
+int full_index(int nw, int full_len)
+{
+	if (nw == 5) return full_len == 150 ? 1 : full_len == 151 ? 2 : full_len == 100 ? 3 : full_len == 101 ? 4 : 0;
+	if (nw == 8) return full_len == 250 ? 1 : full_len == 251 ? 2 : 0;
+	if (nw == 10) return full_len == 300 ? 1 : full_len == 301 ? 2 : 0;
+	return 0;
+}
+
+// n_dev: optional device pointer to the actual pair count (<= n); n then sizes the grid only.
+// full_hint: read length most pairs of the batch are expected to have (0 = unknown); selects the kernel variant only.
 int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride, long long n,
-                spg_result* out, cudaStream_t stream, const int* n_dev = nullptr)
+                spg_result* out, cudaStream_t stream, const int* n_dev = nullptr, int full_hint = -1)
 {
 	if (n <= 0) return SPG_OK;
+	if (full_hint < 0) full_hint = ctx->max_len;
+	if (ctx->full_len >= 0) full_hint = ctx->full_len; // SPG_OPT_FULL_LEN
 	spg::KArgs a;
 	memset(&a, 0, sizeof(a));
 	a.n_dev = n_dev;
@@ -392,7 +407,25 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	int* occ = &d.occ[nw_index(nw)][cw == 2 ? 0 : cw == 4 ? 2 : 1];
 	const long long n_tiles = (n + a.tile_pairs - 1) / a.tile_pairs;
 	cudaError_t e;
-	switch (nw)
+	const int fi = (cw == 3 && full_hint <= stride && !a.force_bytewise) ? full_index(nw, full_hint) : 0;
+	if (fi > 0)
+	{
+		int* focc = &d.full_occ[nw_index(nw)][fi];
+#define SPG_FULL(NW_, FL_) e = launch_cfg<NW_, 3, FL_>(a, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, focc)
+		switch (nw * 8 + fi)
+		{
+			case 5 * 8 + 1: SPG_FULL(5, 150); break;
+			case 5 * 8 + 2: SPG_FULL(5, 151); break;
+			case 5 * 8 + 3: SPG_FULL(5, 100); break;
+			case 5 * 8 + 4: SPG_FULL(5, 101); break;
+			case 8 * 8 + 1: SPG_FULL(8, 250); break;
+			case 8 * 8 + 2: SPG_FULL(8, 251); break;
+			case 10 * 8 + 1: SPG_FULL(10, 300); break;
+			default: SPG_FULL(10, 301); break;
+		}
+#undef SPG_FULL
+	}
+	else switch (nw)
 	{
 		case 5: e = launch_nw<5>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
 		case 8: e = launch_nw<8>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
@@ -772,6 +805,7 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 	{
 		case SPG_OPT_FORCE_BYTEWISE: ctx->force_bytewise = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_GRID_CTAS_PER_SM: ctx->ctas_per_sm = value; return SPG_OK;
+		case SPG_OPT_FULL_LEN: ctx->full_len = value < 0 ? -1 : value; return SPG_OK;
 		case SPG_OPT_MIN_BLOCKS:
 			if (value != 2 && value != 3 && value != 4) return fail(ctx, SPG_ERR_PARAM, "min blocks must be 2, 3 or 4");
 			ctx->min_blocks = value;
@@ -779,12 +813,20 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 		case SPG_OPT_TILE_PAIRS:
 			if (value < 0 || value % 8 != 0 || value > 256) return fail(ctx, SPG_ERR_PARAM, "tile pairs must be a multiple of 8, at most 256");
 			ctx->tile_pairs = value;
-			for (Device& d : ctx->devs) memset(d.occ, 0, sizeof(d.occ));
+			for (Device& d : ctx->devs)
+			{
+				memset(d.occ, 0, sizeof(d.occ));
+				memset(d.full_occ, 0, sizeof(d.full_occ));
+			}
 			return SPG_OK;
 		case SPG_OPT_STAGES:
 			if (value < 0 || value > spg::kMaxStages || value == 1) return fail(ctx, SPG_ERR_PARAM, "stages must be 2..4");
 			ctx->stages = value;
-			for (Device& d : ctx->devs) memset(d.occ, 0, sizeof(d.occ));
+			for (Device& d : ctx->devs)
+			{
+				memset(d.occ, 0, sizeof(d.occ));
+				memset(d.full_occ, 0, sizeof(d.full_occ));
+			}
 			return SPG_OK;
 		default: return fail(ctx, SPG_ERR_PARAM, "unknown option");
 	}

@@ -92,6 +92,28 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a)
 	asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
 	return v;
 }
+// the same with a compile-time byte offset folded into the instruction (no address arithmetic per load)
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u8_at(uint32_t a)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u8 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+	return v;
+}
+template <int OFF>
+__device__ __forceinline__ int lds_s16_at(uint32_t a)
+{
+	int v;
+	asm volatile("ld.shared.s16 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+	return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint2 lds_v2_at(uint32_t a)
+{
+	uint2 v;
+	asm volatile("ld.shared.v2.u32 {%0,%1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(a), "n"(OFF));
+	return v;
+}
 __device__ __forceinline__ void sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)); }
@@ -809,6 +831,241 @@ __device__ __forceinline__ Step123 steps_planes(const KArgs& A, const SmemTables
 	return r;
 }
 
+// ---- full-length fast path ------------------------------------------------------------------------------------------------------------
+// Reads of one sequencing run share one length before trimming. trim_kernel<.., FULL> is compiled for that length: for pairs with
+// len1 == len2 == FULL (and only A/C/G/T) every position test, every window mask of the sweep and every "does the adapter window
+// fit" question is a compile-time constant or a per-lane constant, which the CTA tabulates once in shared memory (FullTab).
+// Any other pair of the batch takes the general path above; the results are the same by construction and are cross-checked
+// against the byte-wise path in the tests.
+__host__ __device__ constexpr int full_qf(int FULL) { return FULL >= 51 ? ((FULL - 51) >> 5) + 1 : 0; } // rounds of the read-1 scan whose 20-base window fits for every lane
+
+template <int NW, int FULL>
+struct FullTab
+{
+	static constexpr int QF = full_qf(FULL) < NW ? full_qf(FULL) : NW;
+	static constexpr int NT = NW - QF > 0 ? NW - QF : 1;
+	int16_t thr[32 * NW]; // [o]: most mismatches with which insert offset o survives the pre-filter (mmin), -1: never
+	uint2 r1tail[NT][32]; // read-1 scan, round QF+t, lane: .x compared adapter positions, .y pass bits by number of mismatches
+	uint2 r2tail[32];     // read-2 scan, last round
+	uint32_t keep2[32];   // read-2 scan: rounds of this lane that start inside the read
+};
+
+template <int NW, int FULL>
+__device__ __forceinline__ void full_tab_init(const KArgs& A, const SmemTables& T, FullTab<NW, FULL>& F, int tid, int nthreads)
+{
+	constexpr int QF = FullTab<NW, FULL>::QF;
+	constexpr int D = 32 * NW - FULL;
+	for (int o = tid; o < 32 * NW; o += nthreads)
+	{
+		const int tot = FULL - o;
+		int t = -1;
+		if (o >= 1 && tot > 0) t = max(tot - (int)T.mmin[tot], -1);
+		F.thr[o] = (int16_t)t;
+	}
+	for (int i = tid; i < 32 * (NW - QF); i += nthreads)
+	{
+		const int q = QF + (i >> 5), l = i & 31;
+		const int cnt = min(A.a_size, FULL - 32 * q - l);
+		const uint32_t valid = low_bits(cnt) & ~A.a1n;
+		F.r1tail[i >> 5][l] = make_uint2(valid, cnt > 0 ? T.passM[__popc(valid)] : 0u);
+	}
+	if (tid < 32)
+	{
+		const uint32_t valid = low_bits(min(A.a_size, 32 - tid)) & ~A.a2n;
+		F.r2tail[tid] = make_uint2(valid, T.passM[__popc(valid)]);
+		F.keep2[tid] = ~low_bits((D - tid + 31) >> 5);
+	}
+}
+
+// planes of a read of length FULL whose position p sits at bit p+D (D = 0: left aligned, D = 32*NW-FULL: right aligned).
+// Loads are unconditional with the word offset folded into the instruction; lanes outside the read may read a neighbouring row
+// of the staged tile (always inside the stage) and are replaced by 'A' where a word is cut by the read's ends.
+template <int NW, int FULL, int D>
+__device__ __forceinline__ uint32_t pack_full(const SmemTables& T, uint32_t row, int lane, Planes<NW>& pl)
+{
+	uint32_t bad = 0;
+	const uint32_t lut = smem_u32(T.not_acgt);
+	const uint32_t base = row + lane - D;
+#pragma unroll
+	for (int w = 0; w < NW; ++w)
+	{
+		const int lo = 32 * w - D, hi = 32 * w + 31 - D; // positions held by lanes 0 and 31
+		if (hi < 0 || lo >= FULL)
+		{
+			pl.h[w] = pl.l[w] = 0;
+			continue;
+		}
+		uint32_t c;
+		switch (w)
+		{
+			case 0: c = lds_u8_at<0>(base); break;
+			case 1: c = lds_u8_at<32>(base); break;
+			case 2: c = lds_u8_at<64>(base); break;
+			case 3: c = lds_u8_at<96>(base); break;
+			case 4: c = lds_u8_at<128>(base); break;
+			case 5: c = lds_u8_at<160>(base); break;
+			case 6: c = lds_u8_at<192>(base); break;
+			case 7: c = lds_u8_at<224>(base); break;
+			case 8: c = lds_u8_at<256>(base); break;
+			default: c = lds_u8_at<288>(base); break;
+		}
+		if (lo < 0 || hi >= FULL) c = ((unsigned)(32 * w + lane - D) < (unsigned)FULL) ? c : (uint32_t)'A';
+		pl.h[w] = ballot_bits(c, 4u);
+		pl.l[w] = ballot_bits(c, 2u);
+		bad |= lds_u8(lut + c);
+	}
+	return bad;
+}
+
+// steps 1-3 for a pair of two FULL-length reads without N (same results as steps_planes<NW,false>)
+template <int NW, int FULL>
+__device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, FULL>& F, const Pair& P, const Planes<NW>& f1, const Planes<NW>& f2r, int lane)
+{
+	constexpr int QF = FullTab<NW, FULL>::QF;
+	Step123 r;
+	r.fwd = r.rev = -1;
+	r.best_offset = -1;
+	// ---- step 1 ----
+	{
+		// revcomp(read 2), shifted right by lane. The complement of the hi plane is folded into the comparison below (xnor), so h
+		// holds the UNcomplemented reversed plane; zeros shifted in at the top then read as mismatches, but only at positions >= FULL.
+		uint32_t h[NW], l[NW], s2h[NW], s2l[NW];
+#pragma unroll
+		for (int w = 0; w < NW; ++w)
+		{
+			h[w] = __brev(f2r.h[NW - 1 - w]);
+			l[w] = __brev(f2r.l[NW - 1 - w]);
+		}
+#pragma unroll
+		for (int w = 0; w < NW; ++w)
+		{
+			s2h[w] = __funnelshift_r(h[w], (w + 1 < NW) ? h[w + 1] : 0u, lane);
+			s2l[w] = __funnelshift_r(l[w], (w + 1 < NW) ? l[w + 1] : 0u, lane);
+		}
+		const uint32_t thr_addr = smem_u32(F.thr) + 2u * (uint32_t)lane;
+		int mmq[NW];
+		bool any = false;
+#pragma unroll
+		for (int q = 0; q < NW; ++q)
+		{
+			int mm = 0;
+#pragma unroll
+			for (int k = 0; k < NW - q; ++k)
+			{
+				const int w = q + k;
+				uint32_t x = ~(s2h[w] ^ f1.h[k]) | (s2l[w] ^ f1.l[k]);
+				if (!(32 * w + 62 < FULL)) // the word holds positions >= FULL - lane for some lane: mask of compared positions (i < FULL - o)
+				{
+					const int n0 = FULL - 32 * w, n1 = FULL - 32 * (w + 1);
+					const uint32_t c0 = n0 >= 32 ? kFull : (n0 <= 0 ? 0u : ((1u << (n0 & 31)) - 1u));
+					const uint32_t c1 = n1 >= 32 ? kFull : (n1 <= 0 ? 0u : ((1u << (n1 & 31)) - 1u));
+					x &= __funnelshift_r(c0, c1, lane);
+				}
+				mm += __popc(x);
+			}
+			mmq[q] = mm;
+			int t;
+			switch (q)
+			{
+				case 0: t = lds_s16_at<0>(thr_addr); break;
+				case 1: t = lds_s16_at<64>(thr_addr); break;
+				case 2: t = lds_s16_at<128>(thr_addr); break;
+				case 3: t = lds_s16_at<192>(thr_addr); break;
+				case 4: t = lds_s16_at<256>(thr_addr); break;
+				case 5: t = lds_s16_at<320>(thr_addr); break;
+				case 6: t = lds_s16_at<384>(thr_addr); break;
+				case 7: t = lds_s16_at<448>(thr_addr); break;
+				case 8: t = lds_s16_at<512>(thr_addr); break;
+				default: t = lds_s16_at<576>(thr_addr); break;
+			}
+			any |= mm <= t;
+		}
+		if (__any_sync(kFull, any)) // rare: about one offset per pair with a real insert match
+		{
+			uint32_t key = kNoKey;
+#pragma unroll
+			for (int q = 0; q < NW; ++q)
+			{
+				uint32_t b = __ballot_sync(kFull, mmq[q] <= (int)F.thr[32 * q + lane]);
+				while (b)
+				{
+					const int src = __ffs(b) - 1;
+					b &= b - 1;
+					const int mm = __shfl_sync(kFull, mmq[q], src);
+					const int tot = FULL - 32 * q - src;
+					key = min(key, candidate_key_warp(A, P, 32 * q + src, tot - mm, mm, lane));
+				}
+			}
+			if (key != kNoKey) r.best_offset = (int)(key & 0xFFFFu);
+		}
+	}
+	if (r.best_offset >= 0) return r;
+	// ---- step 2: read 1 against adapter 1 ----
+	{
+		uint32_t sh[NW], sl[NW], bit[NW];
+		shift_words<NW>(f1.h, lane, sh);
+		shift_words<NW>(f1.l, lane, sl);
+		const uint32_t tail_addr = smem_u32(F.r1tail) + 8u * (uint32_t)lane;
+		uint32_t anyb = 0;
+#pragma unroll
+		for (int q = 0; q < NW; ++q)
+		{
+			const uint32_t x = (sh[q] ^ A.a1h) | (sl[q] ^ A.a1l);
+			if (q < QF) bit[q] = A.a1pass >> __popc(x & A.a1mask);
+			else
+			{
+				uint2 t;
+				switch (q - QF)
+				{
+					case 0: t = lds_v2_at<0>(tail_addr); break;
+					case 1: t = lds_v2_at<256>(tail_addr); break;
+					case 2: t = lds_v2_at<512>(tail_addr); break;
+					case 3: t = lds_v2_at<768>(tail_addr); break;
+					default: t = F.r1tail[q - QF][lane]; break;
+				}
+				bit[q] = t.y >> __popc(x & t.x);
+			}
+			anyb |= bit[q];
+		}
+		if (ballot_bits(anyb, 1u) != 0)
+		{
+			uint32_t pm = 0;
+#pragma unroll
+			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (bit[q] & 1u);
+			const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane) : 0xFFFFFFFFu;
+			r.fwd = (int)__reduce_min_sync(kFull, mine);
+		}
+	}
+	// ---- step 3: read 2 (original orientation, right-aligned planes) against adapter 2 ----
+	{
+		constexpr int D = 32 * NW - FULL;
+		uint32_t sh[NW], sl[NW], bit[NW];
+		shift_words<NW>(f2r.h, lane, sh);
+		shift_words<NW>(f2r.l, lane, sl);
+		const uint2 t = F.r2tail[lane];
+		const uint32_t keep = F.keep2[lane];
+		uint32_t anyb = 0;
+#pragma unroll
+		for (int q = 0; q < NW; ++q)
+		{
+			const uint32_t x = (sh[q] ^ A.a2h) | (sl[q] ^ A.a2l);
+			if (q < NW - 1) bit[q] = A.a2pass >> __popc(x & A.a2mask);
+			else bit[q] = t.y >> __popc(x & t.x);
+			if (32 * q < D) bit[q] &= keep >> q; // rounds that start in the padding in front of the read (32*q + lane < D)
+			anyb |= bit[q];
+		}
+		if (ballot_bits(anyb, 1u) != 0)
+		{
+			uint32_t pm = 0;
+#pragma unroll
+			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (bit[q] & 1u);
+			const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane - D) : 0xFFFFFFFFu;
+			r.rev = (int)__reduce_min_sync(kFull, mine);
+		}
+	}
+	return r;
+}
+
 // pairs in which a byte other than A/C/G/T was seen: N planes, or the byte-wise path for anything else.
 // status: SPG_PAIR_OK or SPG_PAIR_BAD_BASE_R2.
 template <int NW>
@@ -859,15 +1116,27 @@ __device__ __noinline__ RareSteps steps_long(const KArgs& A, const SmemTables& T
 }
 
 // ---- one read pair, one warp ------------------------------------------------------------------------------------------------------------
-template <int NW>
-__device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T, const Pair& P, int lane, spg_result* out, bool& edited)
+template <int NW, int FULL>
+__device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T, const FullTab<(NW > 0 ? NW : 1), (FULL > 0 ? FULL : 1)>& F, const Pair& P, int lane,
+                                             spg_result* out, bool& edited)
 {
 	constexpr int NWP = NW > 0 ? NW : 1;
+	constexpr int FULLP = FULL > 0 ? FULL : 1;
 	int status = SPG_PAIR_OK;
 	bool hasN1 = false, hasN2 = false;
 	Step123 st;
 	bool rare = true;
-	if (NW > 0 && max(P.len1, P.len2) <= 32 * NW && !A.force_bytewise)
+	if (NW > 0 && FULL > 0 && P.len1 == FULL && P.len2 == FULL && !A.force_bytewise)
+	{
+		Planes<NWP> f1, f2r;
+		const uint32_t bad = pack_full<NWP, FULLP, 0>(T, P.r1, lane, f1) | pack_full<NWP, FULLP, 32 * NWP - FULLP>(T, P.r2, lane, f2r);
+		if (ballot_bits(bad, 1u) == 0) // only A/C/G/T in both reads
+		{
+			st = steps_full<NWP, FULLP>(A, F, P, f1, f2r, lane);
+			rare = false;
+		}
+	}
+	else if (NW > 0 && max(P.len1, P.len2) <= 32 * NW && !A.force_bytewise)
 	{
 		Planes<NWP> f1, f2r;
 		const int D2 = 32 * NWP - P.len2; // read 2 is packed right aligned
@@ -965,15 +1234,18 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 // dynamic shared memory: [stages][ b1 | q1 | b2 | q2 : tile_pairs*stride each ][ len1 | len2 : tile_pairs u16 each ]
 // Within a tile the consumer warps claim pairs one at a time from a shared counter, so that a warp that drew cheap pairs
 // (insert hit: no adapter scans) takes more of them and all warps release the stage at about the same time.
-template <int NW, int CW, int MINB>
+// FULL > 0: additionally compiled for pairs of two reads of exactly FULL bases (the fast path above); 0: general code only.
+template <int NW, int CW, int MINB, int FULL = 0>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_constant__ KArgs A)
 {
+	static_assert(FULL == 0 || (NW > 0 && FULL <= 32 * NW && FULL >= 52 && NW - full_qf(FULL) <= 4), "FULL must fit the plane words");
 	constexpr int kThreads = (CW + 1) * 32;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t full_bar[kMaxStages];
 	__shared__ __align__(8) uint64_t empty_bar[kMaxStages];
 	__shared__ int next_pair[kMaxStages];
 	__shared__ SmemTables T;
+	__shared__ FullTab<(NW > 0 ? NW : 1), (FULL > 0 ? FULL : 1)> F;
 
 	const int warp = threadIdx.x >> 5;
 	const int lane = threadIdx.x & 31;
@@ -1004,6 +1276,11 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 		fence_barrier_init();
 	}
 	__syncthreads();
+	if (NW > 0 && FULL > 0)
+	{
+		full_tab_init(A, T, F, (int)threadIdx.x, kThreads);
+		__syncthreads();
+	}
 
 	if (warp == CW)
 	{
@@ -1070,7 +1347,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 				P.len1 = (int)lds_u16(lens + 2u * (uint32_t)pr);
 				P.len2 = (int)lds_u16(lens + 2u * (uint32_t)(TP + pr));
 				bool edited = false;
-				process_pair<NW>(A, T, P, lane, A.out + first + pr, edited);
+				process_pair<NW, FULL>(A, T, F, P, lane, A.out + first + pr, edited);
 				if (edited) // -ec: write the edited rows back
 				{
 					__syncwarp();

@@ -29,13 +29,15 @@ def sp():
     return seqpurge_b200
 
 
-def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, **params):
+def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=None, **params):
     """Run a Batch through spg_submit/spg_wait (pinned slot, H2D, kernel, D2H). Returns records (+ edited batch, ec stats with ec)."""
     p = sp.TrimmingParameters(**params)
     chunk = chunk or batch.n
     eng = sp.Engine(p, devices=(0,), n_slots=n_slots, max_pairs=chunk, max_len=min(batch.stride, 999))
     if force_bytewise:
         eng.set_option(sp.OPT_FORCE_BYTEWISE, 1)
+    if full_len is not None:  # kernel variant compiled for this read length (0: the general kernel)
+        eng.set_option(sp.OPT_FULL_LEN, full_len)
     out = np.zeros(batch.n, sp.RESULT_DTYPE)
     edited = batch.copy() if params.get("ec") else None
     starts = list(range(0, batch.n, chunk))
@@ -260,9 +262,15 @@ def test_device_synthetic_configs(sp, name):
         l2 = torch.empty(n, dtype=torch.int16, device=dev)
         res = torch.empty((n, 8), dtype=torch.uint8, device=dev)
         sp.synth_device(cfg, first, n, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
+        eng.set_option(sp.OPT_FULL_LEN, 0)  # the general kernel ...
+        eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, res)
+        torch.cuda.synchronize()
+        general = sp.results_from_tensor(res).copy()
+        eng.set_option(sp.OPT_FULL_LEN, cfg.read_len)  # ... and the variant compiled for this read length
         eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, res)
         torch.cuda.synchronize()
         got = sp.results_from_tensor(res)
+        assert_same(general, got)
         batch = H.Batch(n, stride)
         for k in t:
             getattr(batch, k)[:n] = t[k].cpu().numpy()
@@ -277,7 +285,7 @@ def test_device_synthetic_configs(sp, name):
 def test_full_size_config2_properties(sp):
     """BASELINE config 2 at its full size (100 M synthetic 2x150 pairs, 10 resident batches of 10 M): properties that do not need the
     oracle on every pair -- the bit-plane path and the byte-wise path (two independent device implementations of the specification)
-    agree on a checksum of checksums, the result is deterministic, every record satisfies the invariants of the trimming rules -- plus
+    agree on a checksum of checksums, the kernel variant compiled for 150-base reads and the general kernel agree on every record, every record satisfies the invariants of the trimming rules -- plus
     the oracle on random 50 k-pair slices of every batch."""
     import torch
 
@@ -301,10 +309,12 @@ def test_full_size_config2_properties(sp):
         l2 = torch.empty(n, dtype=torch.int16, device=dev)
         sp.synth_device(cfg, b * n, n, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
         eng.set_option(sp.OPT_FORCE_BYTEWISE, 0)
+        eng.set_option(sp.OPT_FULL_LEN, L)  # kernel variant compiled for 150-base reads (what bench.py runs)
         eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, res)
+        eng.set_option(sp.OPT_FULL_LEN, 0)  # the general kernel
         eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, res2)
         torch.cuda.synchronize()
-        assert torch.equal(res, res2), "two runs over the same batch differ"
+        assert torch.equal(res, res2), "the full-length variant and the general kernel differ"
         w = res.view(torch.int64).view(-1)
         sums_planes.append(int((w * (torch.arange(n, device=dev) % 1000003 + 1)).sum().item()))
         # invariants of the trimming rules on every record
@@ -365,3 +375,61 @@ def test_parameter_corners(sp, params):
     assert_same(got, want, batch)
     got2, _, _ = gpu_trim(sp, batch, force_bytewise=True, **params)
     assert_same(got2, want, batch)
+
+
+FULL_LENGTHS = [150, 151, 100, 101, 250, 251, 300, 301]
+
+
+def _full_batch(L, seed, n=1536):
+    """Mostly full-length pairs (the fast path of the kernel variant compiled for L), with ragged pairs, N bases and bytes outside
+    ACGTN mixed in (they must leave the fast path) and inserts from far shorter to far longer than the read."""
+    b = H.random_batch(n, L, seed=seed, insert_mean=0.9 * L, insert_sd=0.6 * L, error_rate=0.02, n_rate=0.0003, lowq_tail=6.0, n_runs=0.01)
+    r = H.random_batch(n // 8, L, seed=seed + 1, ragged=True, stride=b.stride)
+    idx = np.random.default_rng(seed).choice(n, n // 8, replace=False)
+    for j, i in enumerate(idx):
+        for k in ("bases1", "quals1", "bases2", "quals2", "len1", "len2"):
+            getattr(b, k)[i] = getattr(r, k)[j]
+    b.bases1[5, 7] = ord("X")  # read 1: compared as a plain byte
+    b.bases2[9, 3] = ord("R")  # read 2: the reference throws
+    return b
+
+
+@pytest.mark.parametrize("L", FULL_LENGTHS)
+def test_full_length_variant(sp, L):
+    """The kernel variants compiled for one read length (pairs of two full-length reads take a path with compile-time masks) against
+    the oracle and against the general kernel."""
+    batch = _full_batch(L, seed=4000 + L)
+    assert int(((batch.len1[: batch.n] == L) & (batch.len2[: batch.n] == L)).sum()) > batch.n // 2
+    want, _ = H.oracle_trim(batch)
+    got, _, _ = gpu_trim(sp, batch, full_len=L)
+    assert_same(got, want, batch)
+    general, _, _ = gpu_trim(sp, batch, full_len=0)
+    assert_same(general, want, batch)
+
+
+@pytest.mark.parametrize("params", [
+    dict(a1="CTGTCTCTTATACACATCT", a2="CTGTCTCTTATACACATCT"),  # a_size 19
+    dict(a1="AGATCGGAAGAGCNCACGTCTGAAC", a2="AGATCGGAAGAGCGTCNTGTAGGGA"),  # N inside the adapters
+    dict(match_perc=70.0, mep=1e-4, qcut=20, qwin=7, ncut=3),
+    dict(adapter_overlap=6, qcut=0, ncut=0),
+], ids=["short_adapters", "adapter_n", "loose", "overlap6"])
+def test_full_length_variant_parameters(sp, params):
+    for L in (150, 251):
+        kw = {k: params[k] for k in ("a1", "a2") if k in params}
+        batch = H.random_batch(1024, L, seed=77 + L, insert_mean=0.9 * L, insert_sd=0.6 * L, error_rate=0.03, n_rate=0.0002, **kw)
+        want, _ = H.oracle_trim(batch, **params)
+        got, _, _ = gpu_trim(sp, batch, full_len=L, **params)
+        assert_same(got, want, batch)
+
+
+def test_full_length_variant_error_correction(sp):
+    params = dict(ec=True)
+    batch = H.random_batch(1024, 150, seed=991, insert_mean=120, insert_sd=40, error_rate=0.03, n_rate=0.0)
+    ref = batch.copy()
+    want, want_ec = H.oracle_trim(ref, **params)
+    got, edited, got_ec = gpu_trim(sp, batch, full_len=150, **params)
+    assert_same(got, want, batch)
+    for name in ("bases1", "quals1", "bases2", "quals2"):
+        assert np.array_equal(getattr(edited, name)[: batch.n], getattr(ref, name)[: batch.n]), name
+    for k in want_ec:
+        assert np.array_equal(got_ec[k], want_ec[k]), k
