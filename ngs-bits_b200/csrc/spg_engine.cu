@@ -295,7 +295,13 @@ void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 	smem = (size_t)stages * (4 * (size_t)tp * stride + 4 * (size_t)tp);
 }
 
-constexpr int kCW = 8; // consumer warps per CTA (+1 producer warp); geometry sweeps showed 4/6/8 within 3%
+#ifndef SPG_CW
+#define SPG_CW 8
+#endif
+#ifndef SPG_FULL_MINB
+#define SPG_FULL_MINB 3 // resident CTAs per SM the read-length variants are compiled for
+#endif
+constexpr int kCW = SPG_CW; // consumer warps per CTA (+1 producer warp); geometry sweeps showed 4/6/8 within 3%
 
 template <int NW, int MINB, int FULL = 0>
 cudaError_t launch_cfg(const spg::KArgs& a, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, int* occ_cache)
@@ -343,6 +349,7 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
                 spg_result* out, cudaStream_t stream, const int* n_dev = nullptr, int full_hint = -1)
 {
 	if (n <= 0) return SPG_OK;
+	if (n > 0x7fffffffLL) return fail(ctx, SPG_ERR_PARAM, "at most 2^31-1 pairs per launch");
 	if (full_hint < 0) full_hint = ctx->max_len;
 	if (ctx->full_len >= 0) full_hint = ctx->full_len; // SPG_OPT_FULL_LEN
 	spg::KArgs a;
@@ -407,11 +414,11 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	int* occ = &d.occ[nw_index(nw)][cw == 2 ? 0 : cw == 4 ? 2 : 1];
 	const long long n_tiles = (n + a.tile_pairs - 1) / a.tile_pairs;
 	cudaError_t e;
-	const int fi = (cw == 3 && full_hint <= stride && !a.force_bytewise) ? full_index(nw, full_hint) : 0;
+	const int fi = (cw == SPG_FULL_MINB && full_hint <= stride && !a.force_bytewise) ? full_index(nw, full_hint) : 0;
 	if (fi > 0)
 	{
 		int* focc = &d.full_occ[nw_index(nw)][fi];
-#define SPG_FULL(NW_, FL_) e = launch_cfg<NW_, 3, FL_>(a, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, focc)
+#define SPG_FULL(NW_, FL_) e = launch_cfg<NW_, SPG_FULL_MINB, FL_>(a, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, focc)
 		switch (nw * 8 + fi)
 		{
 			case 5 * 8 + 1: SPG_FULL(5, 150); break;

@@ -147,6 +147,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
 	             : "memory");
 }
 
+// lane 0 takes the next value of a shared-memory counter; predicated, so the warp does not diverge. Other lanes keep `keep`.
+__device__ __forceinline__ int claim_lane0(uint32_t counter, int lane, int keep)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}" : "+r"(keep) : "r"(lane), "r"(counter) : "memory");
+	return keep;
+}
+// 8-byte store by lane 0 only (predicated, no divergence)
+__device__ __forceinline__ void stg_v2_lane0(void* p, uint32_t x, uint32_t y, int lane)
+{
+	asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %3, 0;\n\t@p st.global.v2.u32 [%0], {%1, %2};\n\t}" ::"l"(p), "r"(x), "r"(y), "r"(lane) : "memory");
+}
+
 // ---- per-pair view of the staged tile: shared-window byte addresses of the four rows ---------------------------------------------------
 struct Pair
 {
@@ -179,6 +191,13 @@ __device__ __forceinline__ uint32_t ballot_bits(uint32_t v, uint32_t bits)
 	uint32_t r;
 	asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tvote.sync.ballot.b32 %0, p, 0xffffffff;\n\t}" : "=r"(r) : "r"(v), "r"(bits));
 	return r;
+}
+// (a ^ b) & c in one LOP3
+__device__ __forceinline__ uint32_t xor_and(uint32_t a, uint32_t b, uint32_t c)
+{
+	uint32_t d;
+	asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+	return d;
 }
 // low `nb` bits set, for any int nb (<=0 -> 0, >=32 -> all)
 __device__ __forceinline__ uint32_t low_bits(int nb) { return __funnelshift_rc(kFull, 0u, (uint32_t)max(32 - nb, 0)); }
@@ -359,34 +378,40 @@ __device__ __forceinline__ void trim_quality_pair(const KArgs& A, const Pair& P,
 	}
 	const bool second = lane >= 16;
 	const int hl = lane & 15;
-	const int base = (second ? n2 : n1) - 16;
+	const int n_r = second ? n2 : n1; // the read this half warp works on
+	const int base = n_r - 16;
 	const int i = base + hl;
 	int v = 0;
 	if (i >= 0) v = qual_at(second ? P.q2 : P.q1, i, A.qoff);
-	int p = v;
+	int s; // window sum q[i] + ... + q[i+window-1], valid for hl <= 16-window
+	if (window == 5) // the default: four independent shuffles instead of a scan (no serial chain)
+	{
+		const int d1 = __shfl_down_sync(kFull, v, 1, 16), d2 = __shfl_down_sync(kFull, v, 2, 16);
+		const int d3 = __shfl_down_sync(kFull, v, 3, 16), d4 = __shfl_down_sync(kFull, v, 4, 16);
+		s = (v + d1 + d2) + (d3 + d4);
+	}
+	else
+	{
+		int p = v;
 #pragma unroll
-	for (int d = 1; d < 16; d <<= 1) // inclusive scan inside each half warp (c = (32-16)<<8: segment width 16)
-		asm volatile("{\n\t.reg .pred g;\n\t.reg .s32 t;\n\tshfl.sync.up.b32 t|g, %0, %1, 0x1000, 0xffffffff;\n\t@g add.s32 %0, %0, t;\n\t}" : "+r"(p) : "r"(d));
-	const int s = __shfl_sync(kFull, p, hl + window - 1, 16) - p + v; // window sum for hl <= 16-window
+		for (int d = 1; d < 16; d <<= 1) // inclusive scan inside each half warp (c = (32-16)<<8: segment width 16)
+			asm volatile("{\n\t.reg .pred g;\n\t.reg .s32 t;\n\tshfl.sync.up.b32 t|g, %0, %1, 0x1000, 0xffffffff;\n\t@g add.s32 %0, %0, t;\n\t}" : "+r"(p) : "r"(d));
+		s = __shfl_sync(kFull, p, hl + window - 1, 16) - p + v;
+	}
 	const uint32_t okm = __ballot_sync(kFull, i >= 0 && hl <= 16 - window && s >= A.qthr);
 	const uint32_t low = __ballot_sync(kFull, i >= 0 && v < A.qcut);
-#pragma unroll
-	for (int r = 0; r < 2; ++r)
-	{
-		const uint32_t ok_r = (okm >> (16 * r)) & 0xFFFFu;
-		const uint32_t low_r = low >> (16 * r);
-		const int n_r = r ? n2 : n1;
-		int res = -1;
-		if (ok_r)
-		{
-			const int t = 31 - __clz(ok_r) + window - 1; // index (0..15) of the last base of the highest passing window
-			const uint32_t x = ~low_r << (31 - t);       // bit 31 = "base t is not low", then downwards; bits above t fall out
-			if (x) res = n_r - 16 + t + 1 - __clz(x);
-		}
-		if (res < 0) res = trim_quality_general(A, r ? P.q2 : P.q1, n_r, lane); // rare: trimming point further left
-		if (r) t2 = res;
-		else t1 = res;
-	}
+	// every lane decodes the votes of its own half (one instruction stream for both reads), lanes 0 and 16 hold the results
+	const uint32_t sh = second ? 16u : 0u;
+	const uint32_t ok_r = (okm >> sh) & 0xFFFFu;
+	const uint32_t low_r = low >> sh;
+	const int t = 31 - __clz(ok_r | 1u) + window - 1; // index (0..15) of the last base of the highest passing window
+	const uint32_t x = ~low_r << (31 - t);            // bit 31 = "base t is not low", then downwards; bits above t fall out
+	int res = n_r - 16 + t + 1 - __clz(x | 1u);
+	if (ok_r == 0 || x == 0) res = -1;                // trimming point further left: rare
+	t1 = __shfl_sync(kFull, res, 0);
+	t2 = __shfl_sync(kFull, res, 16);
+	if (t1 < 0) t1 = trim_quality_general(A, P.q1, n1, lane);
+	if (t2 < 0) t2 = trim_quality_general(A, P.q2, n2, lane);
 }
 
 // ---- FastqEntry::trimN (src/cppNGS/FastqFileStream.cpp:89-117), warp-parallel over run starts; only reads that hold an N get here ----------
@@ -927,43 +952,42 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 	r.best_offset = -1;
 	// ---- step 1 ----
 	{
-		// revcomp(read 2), shifted right by lane. The complement of the hi plane is folded into the comparison below (xnor), so h
-		// holds the UNcomplemented reversed plane; zeros shifted in at the top then read as mismatches, but only at positions >= FULL.
-		uint32_t h[NW], l[NW], s2h[NW], s2l[NW];
+		// Pre-filter on the lo plane alone: two bases that differ in their lo bit are a mismatch, so the number of lo-plane
+		// differences never exceeds the number of mismatches and an offset whose lo-plane count is already above the limit
+		// (F.thr) is out. For unrelated reads half of the lo bits differ against a limit of <= 20 %: about one pair in twenty
+		// keeps a false survivor, which the exact count below then removes.
+		uint32_t l[NW], s2l[NW], mk[NW];
+#pragma unroll
+		for (int w = 0; w < NW; ++w) l[w] = __brev(f2r.l[NW - 1 - w]); // lo plane of revcomp(read 2): the reversed bit string
 #pragma unroll
 		for (int w = 0; w < NW; ++w)
 		{
-			h[w] = __brev(f2r.h[NW - 1 - w]);
-			l[w] = __brev(f2r.l[NW - 1 - w]);
-		}
-#pragma unroll
-		for (int w = 0; w < NW; ++w)
-		{
-			s2h[w] = __funnelshift_r(h[w], (w + 1 < NW) ? h[w + 1] : 0u, lane);
-			s2l[w] = __funnelshift_r(l[w], (w + 1 < NW) ? l[w + 1] : 0u, lane);
+			s2l[w] = __funnelshift_r(l[w], (w + 1 < NW) ? l[w + 1] : 0u, lane); // shifted right by lane: positions 32*w+lane ..
+			mk[w] = kFull;
+			if (!(32 * w + 62 < FULL)) // the word holds positions >= FULL - lane for some lane: mask of compared positions (i < FULL - o)
+			{
+				const int n0 = FULL - 32 * w, n1 = FULL - 32 * (w + 1);
+				const uint32_t c0 = n0 >= 32 ? kFull : (n0 <= 0 ? 0u : ((1u << (n0 & 31)) - 1u));
+				const uint32_t c1 = n1 >= 32 ? kFull : (n1 <= 0 ? 0u : ((1u << (n1 & 31)) - 1u));
+				mk[w] = __funnelshift_r(c0, c1, lane);
+			}
 		}
 		const uint32_t thr_addr = smem_u32(F.thr) + 2u * (uint32_t)lane;
-		int mmq[NW];
+		int mmlq[NW];
 		bool any = false;
 #pragma unroll
 		for (int q = 0; q < NW; ++q)
 		{
-			int mm = 0;
+			int mml = 0;
 #pragma unroll
 			for (int k = 0; k < NW - q; ++k)
 			{
 				const int w = q + k;
-				uint32_t x = ~(s2h[w] ^ f1.h[k]) | (s2l[w] ^ f1.l[k]);
-				if (!(32 * w + 62 < FULL)) // the word holds positions >= FULL - lane for some lane: mask of compared positions (i < FULL - o)
-				{
-					const int n0 = FULL - 32 * w, n1 = FULL - 32 * (w + 1);
-					const uint32_t c0 = n0 >= 32 ? kFull : (n0 <= 0 ? 0u : ((1u << (n0 & 31)) - 1u));
-					const uint32_t c1 = n1 >= 32 ? kFull : (n1 <= 0 ? 0u : ((1u << (n1 & 31)) - 1u));
-					x &= __funnelshift_r(c0, c1, lane);
-				}
-				mm += __popc(x);
+				uint32_t x;
+				if (32 * w + 62 < FULL) x = s2l[w] ^ f1.l[k];
+				else x = xor_and(s2l[w], f1.l[k], mk[w]);
+				mml += __popc(x);
 			}
-			mmq[q] = mm;
 			int t;
 			switch (q)
 			{
@@ -978,22 +1002,40 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 				case 8: t = lds_s16_at<512>(thr_addr); break;
 				default: t = lds_s16_at<576>(thr_addr); break;
 			}
-			any |= mm <= t;
+			mmlq[q] = mml;
+			any |= mml <= t;
 		}
-		if (__any_sync(kFull, any)) // rare: about one offset per pair with a real insert match
+		if (__any_sync(kFull, any)) // pairs with an insert match, and the false survivors of the pre-filter
 		{
+			// exact count for the rounds that hold a survivor. The complement of the hi plane of revcomp(read 2) is folded into
+			// the comparison (xnor), so h is the plain reversed plane; zeros shifted in at the top read as mismatches, but only at
+			// positions >= FULL, which mk removes.
+			uint32_t h[NW], s2h[NW];
+#pragma unroll
+			for (int w = 0; w < NW; ++w) h[w] = __brev(f2r.h[NW - 1 - w]);
+#pragma unroll
+			for (int w = 0; w < NW; ++w) s2h[w] = __funnelshift_r(h[w], (w + 1 < NW) ? h[w + 1] : 0u, lane);
 			uint32_t key = kNoKey;
 #pragma unroll
 			for (int q = 0; q < NW; ++q)
 			{
-				uint32_t b = __ballot_sync(kFull, mmq[q] <= (int)F.thr[32 * q + lane]);
+				const int t = F.thr[32 * q + lane];
+				if (__ballot_sync(kFull, mmlq[q] <= t) == 0) continue;
+				int mm = 0;
+#pragma unroll
+				for (int k = 0; k < NW - q; ++k)
+				{
+					const int w = q + k;
+					mm += __popc((~(s2h[w] ^ f1.h[k]) | (s2l[w] ^ f1.l[k])) & mk[w]);
+				}
+				uint32_t b = __ballot_sync(kFull, mm <= t); // implies the pre-filter: mm >= the lo-plane count
 				while (b)
 				{
 					const int src = __ffs(b) - 1;
 					b &= b - 1;
-					const int mm = __shfl_sync(kFull, mmq[q], src);
+					const int mms = __shfl_sync(kFull, mm, src);
 					const int tot = FULL - 32 * q - src;
-					key = min(key, candidate_key_warp(A, P, 32 * q + src, tot - mm, mm, lane));
+					key = min(key, candidate_key_warp(A, P, 32 * q + src, tot - mms, mms, lane));
 				}
 			}
 			if (key != kNoKey) r.best_offset = (int)(key & 0xFFFFu);
@@ -1212,9 +1254,8 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 			}
 		}
 	}
-	if (lane == 0)
 	{
-		// one 8-byte store: len1 | len2<<16 , best_offset | flags<<16 | status<<24
+		// one 8-byte store by lane 0: len1 | len2<<16 , best_offset | flags<<16 | status<<24 (the values are warp-uniform)
 		uint2 rec;
 		if (status == SPG_PAIR_OK)
 		{
@@ -1226,7 +1267,7 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 			rec.x = 0;
 			rec.y = 0xFFFFu | ((uint32_t)status << 24);
 		}
-		*reinterpret_cast<uint2*>(out) = rec;
+		stg_v2_lane0(out, rec.x, rec.y, lane);
 	}
 }
 
@@ -1252,8 +1293,9 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 	const int TP = A.tile_pairs;
 	const uint32_t plane_bytes = (uint32_t)TP * (uint32_t)A.stride;
 	const uint32_t stage_bytes = 4u * plane_bytes + 4u * (uint32_t)TP;
-	const long long n_pairs = A.n_dev ? (long long)*A.n_dev : A.n_pairs;
-	const long long n_tiles = (n_pairs + TP - 1) / TP;
+	// pair and tile indices fit 32 bits: a launch holds fewer than 2^31 pairs (checked by the host)
+	const uint32_t n_pairs = A.n_dev ? (uint32_t)*A.n_dev : (uint32_t)A.n_pairs;
+	const uint32_t n_tiles = (n_pairs + (uint32_t)TP - 1u) / (uint32_t)TP;
 	const uint32_t smem_base = smem_u32(smem);
 
 	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads) T.mmin[i] = A.mmin[i];
@@ -1288,7 +1330,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 		if (lane == 0)
 		{
 			int it = 0;
-			for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it)
+			for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it)
 			{
 				const int s = it % A.stages;
 				const uint32_t round = (uint32_t)(it / A.stages);
@@ -1297,8 +1339,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 					mbar_wait(&empty_bar[s], (round - 1) & 1u);
 					next_pair[s] = 0; // published to the consumers by the release of the arrive below
 				}
-				const long long first = t * TP;
-				const int cnt = (int)min((long long)TP, n_pairs - first);
+				const uint32_t first = t * (uint32_t)TP;
+				const int cnt = (int)min((uint32_t)TP, n_pairs - first);
 				// bulk copies move multiples of 16 bytes: a ragged last tile (cnt not a multiple of 8) reads up to 14 bytes past its
 				// last row, which stay inside the row planes (they are allocated in multiples of 8 rows)
 				const uint32_t row_bytes = ((uint32_t)cnt * (uint32_t)A.stride + 15u) & ~15u;
@@ -1319,25 +1361,25 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 	{
 		// ===== consumers =====
 		int it = 0;
-		for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it)
+		for (uint32_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it)
 		{
 			const int s = it % A.stages;
 			const uint32_t round = (uint32_t)(it / A.stages);
 			mbar_wait(&full_bar[s], round & 1u);
-			const long long first = t * TP;
-			const int cnt = (int)min((long long)TP, n_pairs - first);
+			const uint32_t first = t * (uint32_t)TP;
+			const int cnt = (int)min((uint32_t)TP, n_pairs - first);
 			const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 			const uint32_t lens = st + 4 * plane_bytes;
 			// lane 0 claims pairs from the tile's counter; the claim for the NEXT pair is issued before the current pair is processed, so
 			// the latency of the shared-memory atomic and of the broadcast is hidden behind a whole pair of work (every warp over-claims
 			// once per tile, which is harmless: the producer resets the counter after all warps have left the stage)
-			int raw = 0x7fffffff;
-			if (lane == 0) raw = atomicAdd(&next_pair[s], 1);
+			const uint32_t counter = smem_u32(&next_pair[s]);
+			int raw = claim_lane0(counter, lane, 0x7fffffff);
 			for (;;)
 			{
 				const int pr = __reduce_min_sync(kFull, raw); // broadcast of lane 0's claim
 				if (pr >= cnt) break;
-				if (lane == 0) raw = atomicAdd(&next_pair[s], 1);
+				raw = claim_lane0(counter, lane, raw);
 				const uint32_t roff = (uint32_t)pr * (uint32_t)A.stride;
 				Pair P;
 				P.r1 = st + roff;
@@ -1347,7 +1389,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 				P.len1 = (int)lds_u16(lens + 2u * (uint32_t)pr);
 				P.len2 = (int)lds_u16(lens + 2u * (uint32_t)(TP + pr));
 				bool edited = false;
-				process_pair<NW, FULL>(A, T, F, P, lane, A.out + first + pr, edited);
+				process_pair<NW, FULL>(A, T, F, P, lane, A.out + (first + (uint32_t)pr), edited);
 				if (edited) // -ec: write the edited rows back
 				{
 					__syncwarp();

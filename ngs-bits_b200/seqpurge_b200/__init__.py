@@ -14,7 +14,7 @@ from dataclasses import dataclass
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libseqpurge_b200.so")
+LIB_PATH = os.environ.get("SPG_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libseqpurge_b200.so")  # SPG_LIB: another build of the same library (kernel experiments)
 
 MAXLEN = 1000
 F_INSERT, F_ADAPTER, F_Q1, F_Q2, F_N1, F_N2 = 1, 2, 4, 8, 16, 32

@@ -39,6 +39,7 @@ for b in range(2):
     bufs.append((t, l1, l2))
 res = torch.empty((n, 8), dtype=torch.uint8, device=dev)
 eng = sp.Engine(params, devices=(0,))
+eng.set_option(sp.OPT_FULL_LEN, int(os.environ.get("SPG_SWEEP_FULL", L)))  # kernel variant compiled for this read length (0: general kernel)
 grid = list(itertools.product((2, 3, 4), (16, 32), (2, 3), (0,)))
 if len(sys.argv) > 3:
     grid = [tuple(int(x) for x in c.split(",")) for c in sys.argv[3:]]
