@@ -403,6 +403,20 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 		};
 		a.a1pass = by_mm(a.a1mask);
 		a.a2pass = by_mm(a.a2mask);
+		// the read-length variants compare mismatch counts with a limit instead of looking a pass bit up: needs adapters without N in
+		// their first a_size bases and pass sets that are intervals 0..k of the mismatch count (they are, for any sane parameters)
+		auto interval = [](uint32_t v) { return (v & (v + 1u)) == 0u; };
+		bool ok = ((a.a1n | a.a2n) & full) == 0u;
+		for (int tot = 0; tot <= ctx->a_size && ok; ++tot)
+		{
+			uint32_t bits = 0;
+			for (int mm = 0; mm <= tot; ++mm)
+				if ((ctx->tables.passA[tot] >> (tot - mm)) & 1u) bits |= 1u << mm;
+			ok = interval(bits);
+		}
+		a.full_ok = ok ? 1 : 0;
+		a.a1maxmm = a.a1pass ? 31 - __builtin_clz(a.a1pass) : -1;
+		a.a2maxmm = a.a2pass ? 31 - __builtin_clz(a.a2pass) : -1;
 	}
 	memset(a.a1, 'N', sizeof(a.a1)); // never read beyond the adapter length: a_size, adapter_overlap <= min(|a1|,|a2|,32)
 	memset(a.a2, 'N', sizeof(a.a2));
@@ -414,7 +428,7 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	int* occ = &d.occ[nw_index(nw)][cw == 2 ? 0 : cw == 4 ? 2 : 1];
 	const long long n_tiles = (n + a.tile_pairs - 1) / a.tile_pairs;
 	cudaError_t e;
-	const int fi = (cw == SPG_FULL_MINB && full_hint <= stride && !a.force_bytewise) ? full_index(nw, full_hint) : 0;
+	const int fi = (cw == SPG_FULL_MINB && full_hint <= stride && !a.force_bytewise && a.full_ok) ? full_index(nw, full_hint) : 0;
 	if (fi > 0)
 	{
 		int* focc = &d.full_occ[nw_index(nw)][fi];

@@ -24,6 +24,10 @@
 
 #include "../../include/seqpurge_b200.h"
 
+#ifndef SPG_STATIC_PAIRS
+#define SPG_STATIC_PAIRS 1 // 1: the pairs of a tile are dealt to the warps round robin instead of being claimed from a counter
+#endif
+
 namespace spg
 {
 
@@ -67,6 +71,8 @@ struct KArgs
 	uint32_t a2h, a2l, a2n;
 	uint32_t a1mask, a2mask; // adapter positions < a_size that are not N
 	uint32_t a1pass, a2pass; // bit j: a full-window comparison (all of amask) with j mismatches passes
+	int a1maxmm, a2maxmm;    // the same as a limit: most mismatches with which a full window passes (-1: never); only valid if full_ok
+	int full_ok;             // adapters without N in their first a_size bases and every pass set of steps 2/3 an interval 0..k of mismatches
 	uint32_t passA[21]; // [T] bit m: adapter-only hit with m matches out of T compared bases passes (steps 2/3)
 	uint8_t a1[32];     // adapter bytes (first 32)
 	uint8_t a2[32];
@@ -870,10 +876,14 @@ struct FullTab
 	static constexpr int QF = full_qf(FULL) < NW ? full_qf(FULL) : NW;
 	static constexpr int NT = NW - QF > 0 ? NW - QF : 1;
 	int16_t thr[32 * NW]; // [o]: most mismatches with which insert offset o survives the pre-filter (mmin), -1: never
-	uint2 r1tail[NT][32]; // read-1 scan, round QF+t, lane: .x compared adapter positions, .y pass bits by number of mismatches
-	uint2 r2tail[32];     // read-2 scan, last round
-	uint32_t keep2[32];   // read-2 scan: rounds of this lane that start inside the read
+	// adapter scans: a window of cnt compared bases is "x << (32-cnt)" (a multiplication by .x = 2^(32-cnt), which runs on the FMA
+	// pipe) and passes with at most .y mismatches (-1: never, e.g. no base left or a round that starts in front of the read)
+	int2 r1tail[NT][32];  // read-1 scan, round QF+t, lane
+	int2 r2tail[32];      // read-2 scan, last round, lane
+	int16_t r2lim[NW][32]; // read-2 scan, round, lane: mismatch limit of a full window, -1 where the round starts in the padding
 };
+
+__device__ __forceinline__ int max_mismatches(uint32_t pass_by_mm) { return 31 - __clz(pass_by_mm); } // pass sets are intervals 0..k (full_ok); 0 -> -1
 
 template <int NW, int FULL>
 __device__ __forceinline__ void full_tab_init(const KArgs& A, const SmemTables& T, FullTab<NW, FULL>& F, int tid, int nthreads)
@@ -891,14 +901,18 @@ __device__ __forceinline__ void full_tab_init(const KArgs& A, const SmemTables& 
 	{
 		const int q = QF + (i >> 5), l = i & 31;
 		const int cnt = min(A.a_size, FULL - 32 * q - l);
-		const uint32_t valid = low_bits(cnt) & ~A.a1n;
-		F.r1tail[i >> 5][l] = make_uint2(valid, cnt > 0 ? T.passM[__popc(valid)] : 0u);
+		F.r1tail[i >> 5][l] = cnt > 0 ? make_int2((int)(1u << (32 - cnt)), max_mismatches(T.passM[cnt])) : make_int2(0, -1);
 	}
-	if (tid < 32)
+	for (int i = tid; i < 32 * NW; i += nthreads)
 	{
-		const uint32_t valid = low_bits(min(A.a_size, 32 - tid)) & ~A.a2n;
-		F.r2tail[tid] = make_uint2(valid, T.passM[__popc(valid)]);
-		F.keep2[tid] = ~low_bits((D - tid + 31) >> 5);
+		const int q = i >> 5, l = i & 31;
+		const bool inside = 32 * q + l >= D; // the round starts inside the read (bits below D are padding)
+		if (q == NW - 1)
+		{
+			const int cnt = min(A.a_size, 32 - l);
+			F.r2tail[l] = inside ? make_int2((int)(1u << (32 - cnt)), max_mismatches(T.passM[cnt])) : make_int2(0, -1);
+		}
+		F.r2lim[q][l] = (int16_t)(inside ? A.a2maxmm : -1);
 	}
 }
 
@@ -1043,17 +1057,25 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 	}
 	if (r.best_offset >= 0) return r;
 	// ---- step 2: read 1 against adapter 1 ----
+	// lane l owns the offsets 32*q+l; the a_size-base window of a round is isolated by a multiplication (a left shift that drops
+	// the bits above it, FMA pipe) and passes with at most a?maxmm mismatches; one vote per read, positions only for hits
+	const uint32_t a1mul = 1u << (32 - A.a_size);
 	{
-		uint32_t sh[NW], sl[NW], bit[NW];
+		uint32_t sh[NW], sl[NW];
+		int mmq[NW];
 		shift_words<NW>(f1.h, lane, sh);
 		shift_words<NW>(f1.l, lane, sl);
 		const uint32_t tail_addr = smem_u32(F.r1tail) + 8u * (uint32_t)lane;
-		uint32_t anyb = 0;
+		bool any = false;
 #pragma unroll
 		for (int q = 0; q < NW; ++q)
 		{
 			const uint32_t x = (sh[q] ^ A.a1h) | (sl[q] ^ A.a1l);
-			if (q < QF) bit[q] = A.a1pass >> __popc(x & A.a1mask);
+			if (q < QF)
+			{
+				mmq[q] = __popc(x * a1mul);
+				any |= mmq[q] <= A.a1maxmm;
+			}
 			else
 			{
 				uint2 t;
@@ -1062,18 +1084,17 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 					case 0: t = lds_v2_at<0>(tail_addr); break;
 					case 1: t = lds_v2_at<256>(tail_addr); break;
 					case 2: t = lds_v2_at<512>(tail_addr); break;
-					case 3: t = lds_v2_at<768>(tail_addr); break;
-					default: t = F.r1tail[q - QF][lane]; break;
+					default: t = lds_v2_at<768>(tail_addr); break;
 				}
-				bit[q] = t.y >> __popc(x & t.x);
+				mmq[q] = __popc(x * t.x);
+				any |= mmq[q] <= (int)t.y;
 			}
-			anyb |= bit[q];
 		}
-		if (ballot_bits(anyb, 1u) != 0)
+		if (__any_sync(kFull, any))
 		{
 			uint32_t pm = 0;
 #pragma unroll
-			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (bit[q] & 1u);
+			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (mmq[q] <= (q < QF ? A.a1maxmm : F.r1tail[q < QF ? 0 : q - QF][lane].y) ? 1u : 0u);
 			const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane) : 0xFFFFFFFFu;
 			r.fwd = (int)__reduce_min_sync(kFull, mine);
 		}
@@ -1081,26 +1102,49 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 	// ---- step 3: read 2 (original orientation, right-aligned planes) against adapter 2 ----
 	{
 		constexpr int D = 32 * NW - FULL;
-		uint32_t sh[NW], sl[NW], bit[NW];
+		uint32_t sh[NW], sl[NW];
+		int mmq[NW];
 		shift_words<NW>(f2r.h, lane, sh);
 		shift_words<NW>(f2r.l, lane, sl);
-		const uint2 t = F.r2tail[lane];
-		const uint32_t keep = F.keep2[lane];
-		uint32_t anyb = 0;
+		const int2 t = F.r2tail[lane];
+		const uint32_t lim_addr = smem_u32(F.r2lim) + 2u * (uint32_t)lane;
+		bool any = false;
 #pragma unroll
 		for (int q = 0; q < NW; ++q)
 		{
 			const uint32_t x = (sh[q] ^ A.a2h) | (sl[q] ^ A.a2l);
-			if (q < NW - 1) bit[q] = A.a2pass >> __popc(x & A.a2mask);
-			else bit[q] = t.y >> __popc(x & t.x);
-			if (32 * q < D) bit[q] &= keep >> q; // rounds that start in the padding in front of the read (32*q + lane < D)
-			anyb |= bit[q];
+			if (32 * q + 31 < D) // the whole round lies in the padding in front of the read
+			{
+				mmq[q] = 0x7fff;
+				continue;
+			}
+			if (q < NW - 1)
+			{
+				mmq[q] = __popc(x * a1mul);
+				int lim = A.a2maxmm;
+				if (32 * q < D) // some lanes of this round start in the padding: per-lane limit
+				{
+					switch (q)
+					{
+						case 0: lim = lds_s16_at<0>(lim_addr); break;
+						case 1: lim = lds_s16_at<64>(lim_addr); break;
+						case 2: lim = lds_s16_at<128>(lim_addr); break;
+						default: lim = F.r2lim[q][lane]; break;
+					}
+				}
+				any |= mmq[q] <= lim;
+			}
+			else
+			{
+				mmq[q] = __popc(x * (uint32_t)t.x);
+				any |= mmq[q] <= t.y;
+			}
 		}
-		if (ballot_bits(anyb, 1u) != 0)
+		if (__any_sync(kFull, any))
 		{
 			uint32_t pm = 0;
 #pragma unroll
-			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (bit[q] & 1u);
+			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (mmq[q] <= (q < NW - 1 ? (int)F.r2lim[q][lane] : t.y) ? 1u : 0u);
 			const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane - D) : 0xFFFFFFFFu;
 			r.rev = (int)__reduce_min_sync(kFull, mine);
 		}
@@ -1168,7 +1212,7 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 	bool hasN1 = false, hasN2 = false;
 	Step123 st;
 	bool rare = true;
-	if (NW > 0 && FULL > 0 && P.len1 == FULL && P.len2 == FULL && !A.force_bytewise)
+	if (NW > 0 && FULL > 0 && P.len1 == FULL && P.len2 == FULL && !A.force_bytewise) // the host picks FULL variants only with A.full_ok
 	{
 		Planes<NWP> f1, f2r;
 		const uint32_t bad = pack_full<NWP, FULLP, 0>(T, P.r1, lane, f1) | pack_full<NWP, FULLP, 32 * NWP - FULLP>(T, P.r2, lane, f2r);
@@ -1370,6 +1414,21 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 			const int cnt = (int)min((uint32_t)TP, n_pairs - first);
 			const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 			const uint32_t lens = st + 4 * plane_bytes;
+#if SPG_STATIC_PAIRS
+			// pairs of a tile are dealt to the consumer warps round robin: no claim, the row addresses advance by additions. The ring
+			// buffers one tile of imbalance between the warps (a warp that is done moves on to the next stage on its own).
+			Pair P;
+			P.r1 = st + (uint32_t)warp * (uint32_t)A.stride;
+			uint32_t lenp = lens + 2u * (uint32_t)warp;
+			spg_result* outp = A.out + (first + (uint32_t)warp);
+			for (int pr = warp; pr < cnt; pr += CW, P.r1 += (uint32_t)CW * (uint32_t)A.stride, lenp += 2u * CW, outp += CW)
+			{
+				P.q1 = P.r1 + plane_bytes;
+				P.r2 = P.r1 + 2 * plane_bytes;
+				P.q2 = P.r1 + 3 * plane_bytes;
+				P.len1 = (int)lds_u16(lenp);
+				P.len2 = (int)lds_u16(lenp + 2u * (uint32_t)TP);
+#else
 			// lane 0 claims pairs from the tile's counter; the claim for the NEXT pair is issued before the current pair is processed, so
 			// the latency of the shared-memory atomic and of the broadcast is hidden behind a whole pair of work (every warp over-claims
 			// once per tile, which is harmless: the producer resets the counter after all warps have left the stage)
@@ -1388,8 +1447,10 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 				P.q2 = st + 3 * plane_bytes + roff;
 				P.len1 = (int)lds_u16(lens + 2u * (uint32_t)pr);
 				P.len2 = (int)lds_u16(lens + 2u * (uint32_t)(TP + pr));
+				spg_result* const outp = A.out + (first + (uint32_t)pr);
+#endif
 				bool edited = false;
-				process_pair<NW, FULL>(A, T, F, P, lane, A.out + (first + (uint32_t)pr), edited);
+				process_pair<NW, FULL>(A, T, F, P, lane, outp, edited);
 				if (edited) // -ec: write the edited rows back
 				{
 					__syncwarp();
