@@ -25,7 +25,11 @@
 #include "../../include/seqpurge_b200.h"
 
 #ifndef SPG_STATIC_PAIRS
-#define SPG_STATIC_PAIRS 1 // 1: the pairs of a tile are dealt to the warps round robin instead of being claimed from a counter
+#define SPG_STATIC_PAIRS 1 // 2: round robin with a claimed tail (measured slower); 1: the pairs of a tile are dealt to the warps round robin instead of being claimed from a counter
+#endif
+
+#ifndef SPG_PRODUCER_SLEEP_NS
+#define SPG_PRODUCER_SLEEP_NS 1000
 #endif
 
 namespace spg
@@ -145,6 +149,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 		    : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
 		    : "memory");
 	} while (!ok);
+}
+// the producer's wait for a stage to be handed back: it has most of a tile's processing time to react, so it polls with real sleeps in
+// between instead of taking issue slots from the consumer warps (try_wait alone came back about 170 times per tile)
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns)
+{
+	for (;;)
+	{
+		uint32_t ok;
+		asm volatile(
+		    "{\n\t.reg .pred p;\n\t"
+		    "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(ok)
+		    : "r"(smem_u32(bar)), "r"(parity)
+		    : "memory");
+		if (ok) break;
+		__nanosleep(sleep_ns);
+	}
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
@@ -1341,6 +1363,12 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 	const uint32_t n_pairs = A.n_dev ? (uint32_t)*A.n_dev : (uint32_t)A.n_pairs;
 	const uint32_t n_tiles = (n_pairs + (uint32_t)TP - 1u) / (uint32_t)TP;
 	const uint32_t smem_base = smem_u32(smem);
+#if SPG_STATIC_PAIRS == 2
+	const int dealt = TP / CW > 1 ? TP / CW - 1 : 0; // pairs per warp and tile that are dealt round robin; the rest of the tile is claimed
+#else
+	const int dealt = 0;
+#endif
+	const int first_claimed = dealt * CW;
 
 	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads) T.mmin[i] = A.mmin[i];
 	for (int i = threadIdx.x; i < 256; i += kThreads) T.not_acgt[i] = (i == 'A' || i == 'C' || i == 'G' || i == 'T') ? 0 : 1;
@@ -1357,7 +1385,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 		{
 			mbar_init(&full_bar[s], 1);
 			mbar_init(&empty_bar[s], CW);
-			next_pair[s] = 0;
+			next_pair[s] = first_claimed;
 		}
 		fence_barrier_init();
 	}
@@ -1380,8 +1408,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 				const uint32_t round = (uint32_t)(it / A.stages);
 				if (round > 0)
 				{
-					mbar_wait(&empty_bar[s], (round - 1) & 1u);
-					next_pair[s] = 0; // published to the consumers by the release of the arrive below
+					mbar_wait_relaxed(&empty_bar[s], (round - 1) & 1u, SPG_PRODUCER_SLEEP_NS);
+					next_pair[s] = first_claimed; // published to the consumers by the release of the arrive below
 				}
 				const uint32_t first = t * (uint32_t)TP;
 				const int cnt = (int)min((uint32_t)TP, n_pairs - first);
@@ -1414,7 +1442,39 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 			const int cnt = (int)min((uint32_t)TP, n_pairs - first);
 			const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 			const uint32_t lens = st + 4 * plane_bytes;
-#if SPG_STATIC_PAIRS
+#if SPG_STATIC_PAIRS == 2
+			// Most pairs of a tile are dealt to the consumer warps round robin (no claim, no atomics); the last TP - dealt*CW pairs are
+			// claimed from a shared counter by whichever warp gets there first, which evens out the differences between the warps once
+			// per tile -- without it the spread between the warps of a CTA grows until the fastest ones wait at the ring all the time.
+			const uint32_t counter = smem_u32(&next_pair[s]);
+			for (int i = 0;;)
+			{
+				int pr;
+				if (i < dealt)
+				{
+					pr = warp + CW * i;
+					++i;
+					if (pr >= cnt) // ragged last tile
+					{
+						i = dealt;
+						continue;
+					}
+				}
+				else
+				{
+					pr = __shfl_sync(kFull, claim_lane0(counter, lane, 0), 0);
+					if (pr >= cnt) break;
+				}
+				const uint32_t roff = (uint32_t)pr * (uint32_t)A.stride;
+				Pair P;
+				P.r1 = st + roff;
+				P.q1 = P.r1 + plane_bytes;
+				P.r2 = P.r1 + 2 * plane_bytes;
+				P.q2 = P.r1 + 3 * plane_bytes;
+				P.len1 = (int)lds_u16(lens + 2u * (uint32_t)pr);
+				P.len2 = (int)lds_u16(lens + 2u * (uint32_t)(TP + pr));
+				spg_result* const outp = A.out + (first + (uint32_t)pr);
+#elif SPG_STATIC_PAIRS == 1
 			// pairs of a tile are dealt to the consumer warps round robin: no claim, the row addresses advance by additions. The ring
 			// buffers one tile of imbalance between the warps (a warp that is done moves on to the next stage on its own).
 			Pair P;
