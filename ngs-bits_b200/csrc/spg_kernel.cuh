@@ -28,6 +28,9 @@
 #define SPG_STATIC_PAIRS 1 // 2: round robin with a claimed tail (measured slower); 1: the pairs of a tile are dealt to the warps round robin instead of being claimed from a counter
 #endif
 
+#ifndef SPG_SPEC_QUALITY
+#define SPG_SPEC_QUALITY 0 // 1: quality trimming of the untrimmed lengths issued ahead of the packing (measured: no gain)
+#endif
 #ifndef SPG_PRODUCER_SLEEP_NS
 #define SPG_PRODUCER_SLEEP_NS 1000
 #endif
@@ -395,15 +398,12 @@ __device__ __forceinline__ int trim_quality_warp(const KArgs& A, uint32_t q, int
 // Both reads of a pair in one pass: lanes 0-15 hold the last 16 qualities of read 1, lanes 16-31 those of read 2 (segmented
 // warp scan of width 16). Covers trimming points within the last 17-window bases of each read; a read that needs more (or a
 // window > 8, or a read shorter than the window) takes trim_quality_warp / trim_quality_general.
-__device__ __forceinline__ void trim_quality_pair(const KArgs& A, const Pair& P, int n1, int n2, int lane, int& t1, int& t2)
+// The core is free of branches for any input (results are only meaningful for window <= 8 <= n1, n2), so that it can also be issued
+// ahead of time for the untrimmed lengths and overlap with the packing of the bases. r1 / r2: new length, or -1 = not decided here.
+template <bool SCAN>
+__device__ __forceinline__ void trim_quality_pair_core(const KArgs& A, const Pair& P, int n1, int n2, int lane, int& r1, int& r2)
 {
 	const int window = A.qwin;
-	if (window > 8 || n1 < window || n2 < window)
-	{
-		t1 = trim_quality_warp(A, P.q1, n1, lane);
-		t2 = trim_quality_warp(A, P.q2, n2, lane);
-		return;
-	}
 	const bool second = lane >= 16;
 	const int hl = lane & 15;
 	const int n_r = second ? n2 : n1; // the read this half warp works on
@@ -412,7 +412,7 @@ __device__ __forceinline__ void trim_quality_pair(const KArgs& A, const Pair& P,
 	int v = 0;
 	if (i >= 0) v = qual_at(second ? P.q2 : P.q1, i, A.qoff);
 	int s; // window sum q[i] + ... + q[i+window-1], valid for hl <= 16-window
-	if (window == 5) // the default: four independent shuffles instead of a scan (no serial chain)
+	if (!SCAN) // window == 5, the default: four independent shuffles instead of a scan (no serial chain)
 	{
 		const int d1 = __shfl_down_sync(kFull, v, 1, 16), d2 = __shfl_down_sync(kFull, v, 2, 16);
 		const int d3 = __shfl_down_sync(kFull, v, 3, 16), d4 = __shfl_down_sync(kFull, v, 4, 16);
@@ -432,12 +432,25 @@ __device__ __forceinline__ void trim_quality_pair(const KArgs& A, const Pair& P,
 	const uint32_t sh = second ? 16u : 0u;
 	const uint32_t ok_r = (okm >> sh) & 0xFFFFu;
 	const uint32_t low_r = low >> sh;
-	const int t = 31 - __clz(ok_r | 1u) + window - 1; // index (0..15) of the last base of the highest passing window
-	const uint32_t x = ~low_r << (31 - t);            // bit 31 = "base t is not low", then downwards; bits above t fall out
+	const int t = (31 - __clz(ok_r | 1u) + window - 1) & 31; // index (0..15) of the last base of the highest passing window
+	const uint32_t x = ~low_r << (31 - t);                   // bit 31 = "base t is not low", then downwards; bits above t fall out
 	int res = n_r - 16 + t + 1 - __clz(x | 1u);
-	if (ok_r == 0 || x == 0) res = -1;                // trimming point further left: rare
-	t1 = __shfl_sync(kFull, res, 0);
-	t2 = __shfl_sync(kFull, res, 16);
+	if (ok_r == 0 || x == 0) res = -1;                       // trimming point further left: rare
+	r1 = __shfl_sync(kFull, res, 0);
+	r2 = __shfl_sync(kFull, res, 16);
+}
+
+__device__ __forceinline__ void trim_quality_pair(const KArgs& A, const Pair& P, int n1, int n2, int lane, int& t1, int& t2)
+{
+	const int window = A.qwin;
+	if (window > 8 || n1 < window || n2 < window)
+	{
+		t1 = trim_quality_warp(A, P.q1, n1, lane);
+		t2 = trim_quality_warp(A, P.q2, n2, lane);
+		return;
+	}
+	if (window == 5) trim_quality_pair_core<false>(A, P, n1, n2, lane, t1, t2);
+	else trim_quality_pair_core<true>(A, P, n1, n2, lane, t1, t2);
 	if (t1 < 0) t1 = trim_quality_general(A, P.q1, n1, lane);
 	if (t2 < 0) t2 = trim_quality_general(A, P.q2, n2, lane);
 }
@@ -979,9 +992,13 @@ __device__ __forceinline__ uint32_t pack_full(const SmemTables& T, uint32_t row,
 }
 
 // steps 1-3 for a pair of two FULL-length reads without N (same results as steps_planes<NW,false>)
+// bad: this lane saw a byte other than A/C/G/T while packing; not_plain is set (and nothing else decided) if any lane did -- the test
+// rides on the vote of the sweep, so that packing and sweep form one stretch of straight-line code.
 template <int NW, int FULL>
-__device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, FULL>& F, const Pair& P, const Planes<NW>& f1, const Planes<NW>& f2r, int lane)
+__device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, FULL>& F, const Pair& P, const Planes<NW>& f1, const Planes<NW>& f2r, uint32_t bad,
+                                              int lane, bool& not_plain)
 {
+	not_plain = false;
 	constexpr int QF = FullTab<NW, FULL>::QF;
 	Step123 r;
 	r.fwd = r.rev = -1;
@@ -1041,8 +1058,13 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 			mmlq[q] = mml;
 			any |= mml <= t;
 		}
-		if (__any_sync(kFull, any)) // pairs with an insert match, and the false survivors of the pre-filter
+		if (__any_sync(kFull, any || (bad & 1u))) // pairs with an insert match, false survivors of the pre-filter, pairs with N etc.
 		{
+			if (__any_sync(kFull, bad & 1u))
+			{
+				not_plain = true;
+				return r;
+			}
 			// exact count for the rounds that hold a survivor. The complement of the hi plane of revcomp(read 2) is folded into
 			// the comparison (xnor), so h is the plain reversed plane; zeros shifted in at the top read as mismatches, but only at
 			// positions >= FULL, which mk removes.
@@ -1082,21 +1104,23 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 	// lane l owns the offsets 32*q+l; the a_size-base window of a round is isolated by a multiplication (a left shift that drops
 	// the bits above it, FMA pipe) and passes with at most a?maxmm mismatches; one vote per read, positions only for hits
 	const uint32_t a1mul = 1u << (32 - A.a_size);
+	constexpr int D = 32 * NW - FULL;
+	int mm1[NW], mm2[NW];
+	bool any1 = false, any2 = false;
+	const int2 t2 = F.r2tail[lane];
 	{
 		uint32_t sh[NW], sl[NW];
-		int mmq[NW];
 		shift_words<NW>(f1.h, lane, sh);
 		shift_words<NW>(f1.l, lane, sl);
 		const uint32_t tail_addr = smem_u32(F.r1tail) + 8u * (uint32_t)lane;
-		bool any = false;
 #pragma unroll
 		for (int q = 0; q < NW; ++q)
 		{
 			const uint32_t x = (sh[q] ^ A.a1h) | (sl[q] ^ A.a1l);
 			if (q < QF)
 			{
-				mmq[q] = __popc(x * a1mul);
-				any |= mmq[q] <= A.a1maxmm;
+				mm1[q] = __popc(x * a1mul);
+				any1 |= mm1[q] <= A.a1maxmm;
 			}
 			else
 			{
@@ -1108,41 +1132,29 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 					case 2: t = lds_v2_at<512>(tail_addr); break;
 					default: t = lds_v2_at<768>(tail_addr); break;
 				}
-				mmq[q] = __popc(x * t.x);
-				any |= mmq[q] <= (int)t.y;
+				mm1[q] = __popc(x * t.x);
+				any1 |= mm1[q] <= (int)t.y;
 			}
-		}
-		if (__any_sync(kFull, any))
-		{
-			uint32_t pm = 0;
-#pragma unroll
-			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (mmq[q] <= (q < QF ? A.a1maxmm : F.r1tail[q < QF ? 0 : q - QF][lane].y) ? 1u : 0u);
-			const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane) : 0xFFFFFFFFu;
-			r.fwd = (int)__reduce_min_sync(kFull, mine);
 		}
 	}
 	// ---- step 3: read 2 (original orientation, right-aligned planes) against adapter 2 ----
 	{
-		constexpr int D = 32 * NW - FULL;
 		uint32_t sh[NW], sl[NW];
-		int mmq[NW];
 		shift_words<NW>(f2r.h, lane, sh);
 		shift_words<NW>(f2r.l, lane, sl);
-		const int2 t = F.r2tail[lane];
 		const uint32_t lim_addr = smem_u32(F.r2lim) + 2u * (uint32_t)lane;
-		bool any = false;
 #pragma unroll
 		for (int q = 0; q < NW; ++q)
 		{
 			const uint32_t x = (sh[q] ^ A.a2h) | (sl[q] ^ A.a2l);
 			if (32 * q + 31 < D) // the whole round lies in the padding in front of the read
 			{
-				mmq[q] = 0x7fff;
+				mm2[q] = 0x7fff;
 				continue;
 			}
 			if (q < NW - 1)
 			{
-				mmq[q] = __popc(x * a1mul);
+				mm2[q] = __popc(x * a1mul);
 				int lim = A.a2maxmm;
 				if (32 * q < D) // some lanes of this round start in the padding: per-lane limit
 				{
@@ -1154,19 +1166,30 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 						default: lim = F.r2lim[q][lane]; break;
 					}
 				}
-				any |= mmq[q] <= lim;
+				any2 |= mm2[q] <= lim;
 			}
 			else
 			{
-				mmq[q] = __popc(x * (uint32_t)t.x);
-				any |= mmq[q] <= t.y;
+				mm2[q] = __popc(x * (uint32_t)t2.x);
+				any2 |= mm2[q] <= t2.y;
 			}
 		}
-		if (__any_sync(kFull, any))
+	}
+	if (__any_sync(kFull, any1 || any2)) // one vote for both reads; the positions are worked out only for hits
+	{
+		if (__any_sync(kFull, any1))
 		{
 			uint32_t pm = 0;
 #pragma unroll
-			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (mmq[q] <= (q < NW - 1 ? (int)F.r2lim[q][lane] : t.y) ? 1u : 0u);
+			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (mm1[q] <= (q < QF ? A.a1maxmm : F.r1tail[q < QF ? 0 : q - QF][lane].y) ? 1u : 0u);
+			const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane) : 0xFFFFFFFFu;
+			r.fwd = (int)__reduce_min_sync(kFull, mine);
+		}
+		if (__any_sync(kFull, any2))
+		{
+			uint32_t pm = 0;
+#pragma unroll
+			for (int q = NW - 1; q >= 0; --q) pm = pm * 2u + (mm2[q] <= (q < NW - 1 ? (int)F.r2lim[q][lane] : t2.y) ? 1u : 0u);
 			const uint32_t mine = pm ? (uint32_t)(32 * (__ffs(pm) - 1) + lane - D) : 0xFFFFFFFFu;
 			r.rev = (int)__reduce_min_sync(kFull, mine);
 		}
@@ -1234,15 +1257,20 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 	bool hasN1 = false, hasN2 = false;
 	Step123 st;
 	bool rare = true;
+	int spec_q1 = -1, spec_q2 = -1; // FULL variants: new lengths by quality trimming if both reads keep all FULL bases (-1: not known)
 	if (NW > 0 && FULL > 0 && P.len1 == FULL && P.len2 == FULL && !A.force_bytewise) // the host picks FULL variants only with A.full_ok
 	{
+		// quality trimming of the untrimmed reads, issued ahead of time: most pairs keep their length through steps 1-3, and the chain
+		// load -> shuffles -> votes -> decode has nothing else to overlap with at the end of the pair (no branches: it merges with the
+		// packing below into one stretch of code)
+#if SPG_SPEC_QUALITY
+		trim_quality_pair_core<true>(A, P, FULL, FULL, lane, spec_q1, spec_q2);
+#endif
 		Planes<NWP> f1, f2r;
 		const uint32_t bad = pack_full<NWP, FULLP, 0>(T, P.r1, lane, f1) | pack_full<NWP, FULLP, 32 * NWP - FULLP>(T, P.r2, lane, f2r);
-		if (ballot_bits(bad, 1u) == 0) // only A/C/G/T in both reads
-		{
-			st = steps_full<NWP, FULLP>(A, F, P, f1, f2r, lane);
-			rare = false;
-		}
+		bool not_plain;
+		st = steps_full<NWP, FULLP>(A, F, P, f1, f2r, bad, lane, not_plain);
+		rare = not_plain; // a byte other than A/C/G/T somewhere
 	}
 	else if (NW > 0 && max(P.len1, P.len2) <= 32 * NW && !A.force_bytewise)
 	{
@@ -1298,7 +1326,12 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 		if (A.qcut > 0) // :430-434
 		{
 			int t1, t2;
-			trim_quality_pair(A, P, n1, n2, lane, t1, t2);
+			if (FULL > 0 && n1 == FULL && n2 == FULL && spec_q1 >= 0 && spec_q2 >= 0 && A.qwin <= 8)
+			{
+				t1 = spec_q1;
+				t2 = spec_q2;
+			}
+			else trim_quality_pair(A, P, n1, n2, lane, t1, t2);
 			if (t1 < n1) flags |= SPG_F_Q1;
 			if (t2 < n2) flags |= SPG_F_Q2;
 			n1 = t1;
@@ -1477,17 +1510,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 #elif SPG_STATIC_PAIRS == 1
 			// pairs of a tile are dealt to the consumer warps round robin: no claim, the row addresses advance by additions. The ring
 			// buffers one tile of imbalance between the warps (a warp that is done moves on to the next stage on its own).
-			Pair P;
-			P.r1 = st + (uint32_t)warp * (uint32_t)A.stride;
-			uint32_t lenp = lens + 2u * (uint32_t)warp;
-			spg_result* outp = A.out + (first + (uint32_t)warp);
-			for (int pr = warp; pr < cnt; pr += CW, P.r1 += (uint32_t)CW * (uint32_t)A.stride, lenp += 2u * CW, outp += CW)
+			// (only the pair index is carried through the loop; everything else is derived from it and from per-tile values)
+			for (int pr = warp; pr < cnt; pr += CW)
 			{
+				Pair P;
+				P.r1 = st + (uint32_t)pr * (uint32_t)A.stride;
 				P.q1 = P.r1 + plane_bytes;
 				P.r2 = P.r1 + 2 * plane_bytes;
 				P.q2 = P.r1 + 3 * plane_bytes;
-				P.len1 = (int)lds_u16(lenp);
-				P.len2 = (int)lds_u16(lenp + 2u * (uint32_t)TP);
+				P.len1 = (int)lds_u16(lens + 2u * (uint32_t)pr);
+				P.len2 = (int)lds_u16(lens + 2u * (uint32_t)(TP + pr));
+				spg_result* const outp = A.out + (first + (uint32_t)pr);
 #else
 			// lane 0 claims pairs from the tile's counter; the claim for the NEXT pair is issued before the current pair is processed, so
 			// the latency of the shared-memory atomic and of the broadcast is hidden behind a whole pair of work (every warp over-claims
