@@ -55,7 +55,8 @@ constexpr size_t kPieceBytes = 1 << 20;      // text per independently deflated 
 constexpr size_t kMaxPendingBytes = 256u << 20; // back-pressure on the producer
 } // namespace
 
-GzipTextWriter::GzipTextWriter(const std::string& filename, int compression_level, WorkerPool* pool) : filename_(filename), level_(compression_level), pool_(pool)
+GzipTextWriter::GzipTextWriter(const std::string& filename, int compression_level, WorkerPool* pool, bool bgzf)
+    : filename_(filename), level_(compression_level), pool_(pool), bgzf_(bgzf)
 {
 	if (compression_level < 0 || compression_level > 9)
 		throw ArgumentException("Invalid gzip compression level '" + std::to_string(compression_level) + "' given for FASTQ file '" + filename + "'!");
@@ -80,7 +81,7 @@ void GzipTextWriter::write(std::vector<uint8_t>&& text)
 	const size_t total = text.size();
 	while (off < total)
 	{
-		const size_t n = pool_ ? std::min(kPieceBytes, total - off) : total;
+		const size_t n = (pool_ || bgzf_) ? std::min(kPieceBytes, total - off) : total;
 		std::unique_ptr<Piece> p(new Piece());
 		if (off == 0 && n == total) p->text = std::move(text);
 		else p->text.assign(text.begin() + (long)off, text.begin() + (long)(off + n));
@@ -94,7 +95,7 @@ void GzipTextWriter::write(std::vector<uint8_t>&& text)
 			if (!pool_) raw->done = true; // the writer thread compresses in order itself
 			queue_.push_back(std::move(p));
 		}
-		if (pool_) pool_->run([this, raw]() { compressPiece(raw); });
+		if (pool_) pool_->run([this, raw]() { bgzf_ ? compressPieceBgzf(raw) : compressPiece(raw); });
 		else cv_.notify_all();
 	}
 }
@@ -132,6 +133,62 @@ void GzipTextWriter::compressPiece(Piece* p)
 	cv_.notify_all();
 }
 
+// the piece as a sequence of BGZF blocks (SAM specification, section 4.1): 18 bytes of header with the block size, raw deflate of at
+// most 0xff00 bytes of text, CRC32, ISIZE
+void GzipTextWriter::compressPieceBgzf(Piece* p)
+{
+	bool failed = false;
+	try
+	{
+		constexpr size_t kBlockText = 0xff00;
+		z_stream zs;
+		memset(&zs, 0, sizeof(zs));
+		if (deflateInit2(&zs, level_, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw Exception("deflateInit2 failed");
+		const size_t n_blocks = (p->text.size() + kBlockText - 1) / kBlockText;
+		p->comp.resize(n_blocks * 65536);
+		size_t out = 0;
+		for (size_t off = 0; off < p->text.size(); off += kBlockText)
+		{
+			const size_t n = std::min(kBlockText, p->text.size() - off);
+			uint8_t* b = p->comp.data() + out;
+			const uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
+			memcpy(b, hdr, 18);
+			deflateReset(&zs);
+			zs.next_in = p->text.data() + off;
+			zs.avail_in = (uInt)n;
+			zs.next_out = b + 18;
+			zs.avail_out = 65536 - 18 - 8;
+			if (deflate(&zs, Z_FINISH) != Z_STREAM_END)
+			{
+				deflateEnd(&zs);
+				throw Exception("deflate failed for '" + filename_ + "'");
+			}
+			const size_t clen = (65536 - 18 - 8) - zs.avail_out;
+			const size_t bsize = 18 + clen + 8;
+			b[16] = (uint8_t)((bsize - 1) & 0xff);
+			b[17] = (uint8_t)((bsize - 1) >> 8);
+			const uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), p->text.data() + off, (uInt)n);
+			for (int i = 0; i < 4; ++i) b[18 + clen + i] = (uint8_t)(crc >> (8 * i));
+			for (int i = 0; i < 4; ++i) b[18 + clen + 4 + i] = (uint8_t)((uint32_t)n >> (8 * i));
+			out += bsize;
+		}
+		deflateEnd(&zs);
+		p->comp.resize(out);
+	}
+	catch (...)
+	{
+		failed = true;
+		std::lock_guard<std::mutex> g(mu_);
+		if (!failure_) failure_ = std::current_exception();
+	}
+	(void)failed;
+	{
+		std::lock_guard<std::mutex> g(mu_);
+		p->done = true;
+	}
+	cv_.notify_all();
+}
+
 void GzipTextWriter::writerLoop()
 {
 	gzFile gz = nullptr;
@@ -140,7 +197,7 @@ void GzipTextWriter::writerLoop()
 	uint64_t isize = 0;
 	try
 	{
-		if (!pool_)
+		if (!pool_ && !bgzf_)
 		{
 			gz = gzopen(filename_.c_str(), "wb");
 			if (!gz) throw FileAccessException("Could not open file '" + filename_ + "' for writing!");
@@ -154,7 +211,7 @@ void GzipTextWriter::writerLoop()
 			// the header zlib's gzopen("wb") writes: no name, no time, XFL as deflate sets it, OS = Unix
 			const unsigned char xfl = level_ == 9 ? 2 : (level_ < 2 ? 4 : 0);
 			const unsigned char hdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, xfl, 3};
-			if (fwrite(hdr, 1, 10, fp) != 10) throw FileAccessException("Could not write to file '" + filename_ + "'!");
+			if (!bgzf_ && fwrite(hdr, 1, 10, fp) != 10) throw FileAccessException("Could not write to file '" + filename_ + "'!");
 		}
 		for (;;)
 		{
@@ -167,7 +224,8 @@ void GzipTextWriter::writerLoop()
 				p = std::move(queue_.front());
 				queue_.pop_front();
 			}
-			if (!pool_)
+			if (bgzf_ && !pool_) compressPieceBgzf(p.get()); // serial BGZF: deflate here, in order
+			if (gz)
 			{
 				size_t off = 0; // gzwrite takes an unsigned length
 				while (off < p->text.size())
@@ -199,7 +257,8 @@ void GzipTextWriter::writerLoop()
 			unsigned char tail[10] = {0x03, 0x00}; // empty static block with BFINAL, then CRC32 and ISIZE (little endian)
 			for (int i = 0; i < 4; ++i) tail[2 + i] = (unsigned char)(crc >> (8 * i));
 			for (int i = 0; i < 4; ++i) tail[6 + i] = (unsigned char)((uint32_t)isize >> (8 * i));
-			const bool ok = fwrite(tail, 1, 10, fp) == 10;
+			static const unsigned char bgzf_eof[28] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0x1b, 0, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+			const bool ok = bgzf_ ? fwrite(bgzf_eof, 1, 28, fp) == 28 : fwrite(tail, 1, 10, fp) == 10;
 			const bool closed = fclose(fp) == 0;
 			fp = nullptr;
 			if (!ok || !closed) throw FileAccessException("Could not write to file '" + filename_ + "'!");

@@ -3,6 +3,9 @@
 // threads == 1: the zlib call sequence of the reference's FastqOutfileStream (src/cppNGS/FastqFileStream.cpp:160-172: gzopen "wb",
 //   gzbuffer 131072, gzsetparams) fed by one writer thread per file, like the reference's FastqWriter threads
 //   (src/SeqPurge/OutputWorker.cpp:24-32) -- the .gz bytes equal the reference's for equal records.
+// bgzf: the output is written as BGZF (blocked gzip as htslib/bgzip write it: members of at most 64 KiB that carry their compressed
+//   size in a 'BC' extra field, plus the empty end-of-file block), with or without a pool. Any gzip reader reads it; this
+//   repository's TextSource and htslib inflate it in parallel.
 // threads  > 1: the text is cut into pieces that a shared pool deflates independently (raw deflate, Z_SYNC_FLUSH), written in order
 //   as ONE gzip member (header, pieces, empty final block, CRC32/ISIZE trailer; CRCs joined with crc32_combine). The decompressed
 //   content is identical, the compressed bytes are not (and a little larger: no matches across piece boundaries).
@@ -41,7 +44,7 @@ class GzipTextWriter
 {
 public:
 	// pool == nullptr: serial zlib stream (reference byte sequence)
-	GzipTextWriter(const std::string& filename, int compression_level, WorkerPool* pool);
+	GzipTextWriter(const std::string& filename, int compression_level, WorkerPool* pool, bool bgzf = false);
 	~GzipTextWriter();
 	GzipTextWriter(const GzipTextWriter&) = delete;
 	GzipTextWriter& operator=(const GzipTextWriter&) = delete;
@@ -58,10 +61,12 @@ private:
 	};
 	void writerLoop();
 	void compressPiece(Piece* p);
+	void compressPieceBgzf(Piece* p);
 
 	std::string filename_;
 	int level_;
 	WorkerPool* pool_;
+	bool bgzf_ = false;
 	std::mutex mu_;
 	std::condition_variable cv_;
 	std::deque<std::unique_ptr<Piece>> queue_; // in output order

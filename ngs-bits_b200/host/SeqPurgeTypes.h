@@ -98,6 +98,7 @@ struct TrimmingParameters
 	int compression_level = 1; // Z_BEST_SPEED
 	std::string qc;
 	std::vector<int> gpus = {0}; // new, behaviour-neutral: CUDA devices the blocks are dealt to round robin
+	bool bgzf = false;           // new: outputs are written as BGZF (blocked gzip); stream pipeline only
 	bool host_framing = false;   // new: FASTQ records are parsed/formatted on the host (block pipeline of the reference) instead of on the device
 };
 

@@ -24,6 +24,7 @@
 #include "GpuAnalysisWorker.h"
 #include "GzipTextWriter.h"
 #include "QcReport.h"
+#include "TextSource.h"
 
 namespace seqpurge
 {
@@ -91,16 +92,14 @@ private:
 };
 
 // reads the files of one list, cuts the inflated text after every `pairs` records
-void readerLoop(const std::vector<std::string>& files, int pairs, ChunkQueue& out)
+void readerLoop(const std::vector<std::string>& files, int pairs, ChunkQueue& out, WorkerPool* pool)
 {
 	try
 	{
 		std::vector<uint8_t> buf((size_t)4 << 20);
 		for (size_t fi = 0; fi < files.size(); ++fi)
 		{
-			gzFile gz = gzopen(files[fi].c_str(), "rb");
-			if (!gz) throw FileAccessException("Could not open file '" + files[fi] + "' for reading!");
-			gzbuffer(gz, 1 << 20);
+			std::unique_ptr<TextSource> src = openTextSource(files[fi], pool); // BGZF inputs are inflated by the pool, anything else by gzFile
 			std::unique_ptr<TextChunk> cur(new TextChunk());
 			cur->file_index = fi;
 			long long lines = 0;   // complete lines in cur
@@ -108,15 +107,7 @@ void readerLoop(const std::vector<std::string>& files, int pairs, ChunkQueue& ou
 			const long long cut = 4ll * pairs;
 			for (;;)
 			{
-				const int n = gzread(gz, buf.data(), (unsigned)buf.size());
-				if (n < 0)
-				{
-					int err = Z_OK;
-					const char* msg = gzerror(gz, &err);
-					const std::string m = msg ? msg : "";
-					gzclose(gz);
-					throw FileParseException("Error while reading file '" + files[fi] + "': " + m);
-				}
+				const size_t n = src->read(buf.data(), buf.size());
 				if (n == 0) break;
 				const uint8_t* p = buf.data();
 				const uint8_t* end = p + n;
@@ -147,7 +138,7 @@ void readerLoop(const std::vector<std::string>& files, int pairs, ChunkQueue& ou
 				}
 				cur->data.insert(cur->data.end(), start, end);
 			}
-			gzclose(gz);
+			src.reset();
 			if (line_len > 0) // unterminated last line
 			{
 				if (lines & 1) cur->max_read_len = (int)std::min<size_t>(std::max<size_t>((size_t)cur->max_read_len, line_len), 1u << 30);
@@ -255,17 +246,17 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 	std::unique_ptr<WorkerPool> pool;
 	if (params.threads > 1) pool.reset(new WorkerPool(params.threads));
 	std::unique_ptr<GzipTextWriter> writers[4];
-	writers[0].reset(new GzipTextWriter(params.out1, params.compression_level, pool.get()));
-	writers[1].reset(new GzipTextWriter(params.out2, params.compression_level, pool.get()));
+	writers[0].reset(new GzipTextWriter(params.out1, params.compression_level, pool.get(), params.bgzf));
+	writers[1].reset(new GzipTextWriter(params.out2, params.compression_level, pool.get(), params.bgzf));
 	if (singles)
 	{
-		writers[2].reset(new GzipTextWriter(params.out3 + "_R1.fastq.gz", params.compression_level, pool.get()));
-		writers[3].reset(new GzipTextWriter(params.out3 + "_R2.fastq.gz", params.compression_level, pool.get()));
+		writers[2].reset(new GzipTextWriter(params.out3 + "_R1.fastq.gz", params.compression_level, pool.get(), params.bgzf));
+		writers[3].reset(new GzipTextWriter(params.out3 + "_R2.fastq.gz", params.compression_level, pool.get(), params.bgzf));
 	}
 
 	ChunkQueue q1(4), q2(4);
-	std::thread reader1([&]() { readerLoop(params.files_in1, pairs, q1); });
-	std::thread reader2([&]() { readerLoop(params.files_in2, pairs, q2); });
+	std::thread reader1([&]() { readerLoop(params.files_in1, pairs, q1, pool.get()); });
+	std::thread reader2([&]() { readerLoop(params.files_in2, pairs, q2, pool.get()); });
 	struct ReaderGuard
 	{
 		ChunkQueue &a, &b;

@@ -150,6 +150,8 @@ void usage()
 	             "          -out3 <prefix> -summary <file> -qc <file.qcML> -block_size 10000 -block_prefetch 32 -ec -compression_level 1\n"
 	             "New: -gpus 0[,1,...]  CUDA devices the blocks are dealt to (default 0)\n"
 	             "     -threads N       N > 1: the output files are deflated by N threads (same content, different .gz bytes)\n"
+	             "     -bgzf            write the outputs as BGZF (blocked gzip, readable by any gzip reader, inflatable in parallel); BGZF inputs\n"
+	             "                      are inflated by the -threads pool\n"
 	             "     -host_framing    parse and format FASTQ records on the host (the reference's block pipeline) instead of on the device\n";
 }
 
@@ -199,6 +201,7 @@ int main(int argc, char** argv)
 			else if (f == "-gpus") params.gpus = parseIntList(next());
 			else if (f == "-qc") params.qc = next();
 			else if (f == "-host_framing") params.host_framing = true;
+			else if (f == "-bgzf") params.bgzf = true;
 			else if (f == "-debug") throw CommandLineParsingException("Parameter '" + f + "' is not supported by seqpurge_b200.");
 			else throw CommandLineParsingException("Unknown parameter '" + f + "'!");
 		}

@@ -54,6 +54,11 @@ plain = {}
 for r in (1, 2):  # uncompressed copies of the inputs: the inflate-free upper bound of the pipeline
     plain[r] = f"{d}/in{r}.fastq"
     subprocess.run(f"gzip -dc {d}/in{r}.fastq.gz > {plain[r]}", shell=True, check=True)
+bgz = {}
+pipe = os.path.join(ROOT, "ngs-bits_b200", "bin", "gzpipe")
+for r in (1, 2):  # the same inputs as BGZF (blocked gzip): inflated by the -threads pool
+    bgz[r] = f"{d}/in{r}.bgzf.fastq.gz"
+    subprocess.run([pipe, plain[r], bgz[r], "-bgzf", "-threads", str(threads)], check=True, stderr=subprocess.DEVNULL)
 runs = {
     "oracle_cli": ([os.path.join(ROOT, "oracle", "build", "seqpurge_oracle"), "-threads", str(threads)], "gz"),
     "b200_host_framing": ([cli, "-host_framing"], "gz"),
@@ -61,10 +66,15 @@ runs = {
     f"b200_deflate_threads_{threads}": ([cli, "-threads", str(threads), "-block_size", "32768"], "gz"),
     f"b200_plain_in_deflate_threads_{threads}": ([cli, "-threads", str(threads), "-block_size", "32768"], "plain"),
     f"b200_plain_in_level0_out_threads_{threads}": ([cli, "-threads", str(threads), "-block_size", "32768", "-compression_level", "0"], "plain"),
+    f"b200_bgzf_in_threads_{threads}": ([cli, "-threads", str(threads), "-block_size", "32768"], "bgzf"),
+    f"b200_bgzf_in_bgzf_out_threads_{threads}": ([cli, "-threads", str(threads), "-block_size", "32768", "-bgzf"], "bgzf"),
 }
+if os.environ.get("SPG_CLI_ONLY"):  # comma-separated run names (the oracle CLI alone takes half a minute)
+    keep = set(os.environ["SPG_CLI_ONLY"].split(",")) | {"oracle_cli"}
+    runs = {k: v for k, v in runs.items() if k in keep or any(k.startswith(x) for x in keep)}
 for name, (cmd, kind) in runs.items():
     os.makedirs(f"{d}/{name}")
-    in1, in2 = (f"{d}/in1.fastq.gz", f"{d}/in2.fastq.gz") if kind == "gz" else (plain[1], plain[2])
+    in1, in2 = (f"{d}/in1.fastq.gz", f"{d}/in2.fastq.gz") if kind == "gz" else ((bgz[1], bgz[2]) if kind == "bgzf" else (plain[1], plain[2]))
     t0 = time.perf_counter()
     subprocess.run(cmd + ["-in1", in1, "-in2", in2, "-out1", f"{d}/{name}/o1.fastq.gz", "-out2", f"{d}/{name}/o2.fastq.gz", "-summary", f"{d}/{name}/s.txt"], check=True)
     el = time.perf_counter() - t0

@@ -135,3 +135,22 @@ def test_cli_config1_synthetic_10k_gz_byte_identical(cli, oracle_build, tmp_path
     for name in ("o1.fastq.gz", "o2.fastq.gz", "single_R1.fastq.gz", "single_R2.fastq.gz"):
         assert _raw(outs["gpu"] / name) == _raw(outs["oracle"] / name), name
     assert len(_content(outs["gpu"] / "o1.fastq.gz")) > 1_000_000
+
+
+def test_cli_bgzf_out_and_parallel_bgzf_in(cli, tmp_path):
+    """-bgzf writes blocked gzip (decompressed content = the reference's golden files); BGZF inputs are inflated by the -threads pool
+    and give the same output as the original gzip inputs."""
+    d = tmp_path
+    base = [cli, "-summary", str(d / "s.txt"), "-ncut", "0", "-qcut", "0", "-min_len", "15"]
+    subprocess.run(base + ["-in1", f"{G}/SeqPurge_in1.fastq.gz", "-in2", f"{G}/SeqPurge_in2.fastq.gz", "-out1", str(d / "o1.gz"), "-out2", str(d / "o2.gz"),
+                           "-bgzf", "-threads", "4"], check=True)
+    assert _content(d / "o1.gz") == _content(f"{G}/SeqPurge_out1.fastq.gz")
+    assert _content(d / "o2.gz") == _content(f"{G}/SeqPurge_out2.fastq.gz")
+    assert _raw(d / "o1.gz")[:4] == b"\x1f\x8b\x08\x04" and _raw(d / "o1.gz")[12:16] == b"BC\x02\x00"
+    # the inputs re-blocked as BGZF (bin/gzpipe), then trimmed with parallel inflate
+    pipe = os.path.join(ROOT, "ngs-bits_b200", "bin", "gzpipe")
+    for r in (1, 2):
+        subprocess.run([pipe, f"{G}/SeqPurge_in{r}.fastq.gz", str(d / f"in{r}.bgzf.gz"), "-bgzf", "-threads", "2"], check=True)
+    subprocess.run(base + ["-in1", str(d / "in1.bgzf.gz"), "-in2", str(d / "in2.bgzf.gz"), "-out1", str(d / "p1.gz"), "-out2", str(d / "p2.gz"), "-threads", "4"], check=True)
+    assert _content(d / "p1.gz") == _content(f"{G}/SeqPurge_out1.fastq.gz")
+    assert _content(d / "p2.gz") == _content(f"{G}/SeqPurge_out2.fastq.gz")
