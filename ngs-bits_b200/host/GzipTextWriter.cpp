@@ -77,27 +77,36 @@ GzipTextWriter::~GzipTextWriter()
 void GzipTextWriter::write(std::vector<uint8_t>&& text)
 {
 	if (text.empty()) return;
+	if (!pool_ && !bgzf_) enqueue(std::move(text)); // one piece, no copy
+	else write(text.data(), text.size());
+}
+
+void GzipTextWriter::write(const uint8_t* text, size_t total)
+{
 	size_t off = 0;
-	const size_t total = text.size();
 	while (off < total)
 	{
 		const size_t n = (pool_ || bgzf_) ? std::min(kPieceBytes, total - off) : total;
-		std::unique_ptr<Piece> p(new Piece());
-		if (off == 0 && n == total) p->text = std::move(text);
-		else p->text.assign(text.begin() + (long)off, text.begin() + (long)(off + n));
+		enqueue(std::vector<uint8_t>(text + off, text + off + n));
 		off += n;
-		Piece* raw = p.get();
-		{
-			std::unique_lock<std::mutex> l(mu_);
-			cv_.wait(l, [this] { return pending_bytes_ < kMaxPendingBytes || failure_; });
-			if (failure_) std::rethrow_exception(failure_);
-			pending_bytes_ += raw->text.size();
-			if (!pool_) raw->done = true; // the writer thread compresses in order itself
-			queue_.push_back(std::move(p));
-		}
-		if (pool_) pool_->run([this, raw]() { bgzf_ ? compressPieceBgzf(raw) : compressPiece(raw); });
-		else cv_.notify_all();
 	}
+}
+
+void GzipTextWriter::enqueue(std::vector<uint8_t>&& text)
+{
+	std::unique_ptr<Piece> p(new Piece());
+	p->text = std::move(text);
+	Piece* raw = p.get();
+	{
+		std::unique_lock<std::mutex> l(mu_);
+		cv_.wait(l, [this] { return pending_bytes_ < kMaxPendingBytes || failure_; });
+		if (failure_) std::rethrow_exception(failure_);
+		pending_bytes_ += raw->text.size();
+		if (!pool_) raw->done = true; // the writer thread compresses in order itself
+		queue_.push_back(std::move(p));
+	}
+	if (pool_) pool_->run([this, raw]() { bgzf_ ? compressPieceBgzf(raw) : compressPiece(raw); });
+	else cv_.notify_all();
 }
 
 void GzipTextWriter::compressPiece(Piece* p)

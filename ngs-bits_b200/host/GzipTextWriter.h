@@ -50,6 +50,7 @@ public:
 	GzipTextWriter& operator=(const GzipTextWriter&) = delete;
 
 	void write(std::vector<uint8_t>&& text); // called from one thread, in output order; blocks when too much is pending
+	void write(const uint8_t* text, size_t n); // the same from a buffer the caller keeps (copied once, piece by piece)
 	void close();                            // waits for everything to be on disk; throws what the writer thread met
 
 private:
@@ -59,6 +60,7 @@ private:
 		uint32_t crc = 0;
 		bool done = false;
 	};
+	void enqueue(std::vector<uint8_t>&& text);
 	void writerLoop();
 	void compressPiece(Piece* p);
 	void compressPieceBgzf(Piece* p);

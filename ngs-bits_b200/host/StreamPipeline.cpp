@@ -231,18 +231,6 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 	const int n_slots = std::max(2, std::min(params.block_prefetch, 4)) * (int)params.gpus.size(); // chunks in flight: the GPU part of a chunk is far shorter than its inflate
 	(void)summary;
 
-	spg_params ep = toEngineParams(params);
-	spg_ctx* engine = nullptr;
-	if (spg_create(&engine, &ep, params.gpus.data(), (int)params.gpus.size(), 0, 0, 0) != SPG_OK)
-		throw Exception(std::string("Could not initialize the CUDA trimming engine: ") + spg_last_error(nullptr));
-	struct EngineGuard
-	{
-		spg_ctx* e;
-		~EngineGuard() { spg_destroy(e); }
-	} engine_guard{engine};
-
-	t_init += since(tp);
-
 	std::unique_ptr<WorkerPool> pool;
 	if (params.threads > 1) pool.reset(new WorkerPool(params.threads));
 	std::unique_ptr<GzipTextWriter> writers[4];
@@ -269,6 +257,20 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 			if (t2.joinable()) t2.join();
 		}
 	} reader_guard{q1, q2, reader1, reader2};
+
+	// the engine comes up (CUDA context, decision tables) while the readers already inflate
+	spg_params ep = toEngineParams(params);
+	spg_ctx* engine = nullptr;
+	if (spg_create(&engine, &ep, params.gpus.data(), (int)params.gpus.size(), 0, 0, 0) != SPG_OK)
+		throw Exception(std::string("Could not initialize the CUDA trimming engine: ") + spg_last_error(nullptr));
+	struct EngineGuard
+	{
+		spg_ctx* e;
+		~EngineGuard() { spg_destroy(e); }
+	} engine_guard{engine};
+
+
+	t_init += since(tp);
 
 	spg_fq* fq = nullptr;
 	int fq_max_len = 0;
@@ -340,7 +342,7 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 		t_stats += since(t0);
 		t0 = clk::now();
 		for (int k = 0; k < 4; ++k)
-			if (writers[k] && o.out_bytes[k] > 0) writers[k]->write(std::vector<uint8_t>(o.out[k], o.out[k] + o.out_bytes[k]));
+			if (writers[k] && o.out_bytes[k] > 0) writers[k]->write(o.out[k], (size_t)o.out_bytes[k]);
 		t_write += since(t0);
 	};
 
