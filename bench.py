@@ -125,7 +125,25 @@ def best_oracle_threads(H, probe, **params):
     return best[1], best[0]
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line of this run, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries write to fd 1 on their own (NCCL prints its version line there under torchrun): keep stdout for the JSON line only
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -209,7 +227,7 @@ def main():
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------------------------------------ this repo's engine
@@ -335,7 +353,7 @@ def main():
         line["e2e"] = e2e
     if cpu:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line))
+    emit(line)
     if dist:
         dist.destroy_process_group()
     eng.close()
