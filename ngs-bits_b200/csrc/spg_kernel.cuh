@@ -4,8 +4,8 @@
 // (src/SeqPurge/AnalysisWorker.cpp:122-441); the numbered steps in the comments are the reference's.
 // Nothing here is derived from the reference's code structure: the reference walks bytes offset by offset, this kernel
 //   * stages tiles of pairs (ASCII rows, as FASTQ delivers them) into shared memory with 1-D TMA bulk copies
-//     (cp.async.bulk + mbarrier, a dedicated producer warp, NS-deep ring); consumer warps claim pairs of the staged tile
-//     from a shared counter,
+//     (cp.async.bulk + mbarrier, a dedicated producer warp, NS-deep ring); the pairs of a staged tile are dealt to the
+//     consumer warps round robin,
 //   * packs every read into two bit planes (hi/lo bit of a 2-bit base code) with warp ballots; every lane then holds the
 //     whole read in registers. Read 2 is packed right-aligned, so that revcomp(read 2) is just the reversed bit string
 //     (BREV per word) with the hi plane complemented -- no second pass over its bytes,
@@ -17,20 +17,17 @@
 //     and every decision is bit-exact,
 //   * keeps everything unusual (N bases, bytes outside ACGTN, reads longer than the plane path, -ec, N trimming) in
 //     non-inlined functions so that the common path stays small enough for the instruction cache; the byte-wise path
-//     mirrors the specification directly and doubles as the on-device cross-check of the plane path.
+//     mirrors the specification directly and doubles as the on-device cross-check of the plane path,
+//   * is additionally compiled for the read length of the run (template parameter FULL): pairs of two full-length reads take
+//     steps_full, where position tests are compile-time or per-lane constants, the sweep first bounds the mismatch count from
+//     below with one bit plane, and the adapter windows are isolated on the FMA pipe.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include "../../include/seqpurge_b200.h"
 
-#ifndef SPG_STATIC_PAIRS
-#define SPG_STATIC_PAIRS 1 // 2: round robin with a claimed tail (measured slower); 1: the pairs of a tile are dealt to the warps round robin instead of being claimed from a counter
-#endif
 
-#ifndef SPG_SPEC_QUALITY
-#define SPG_SPEC_QUALITY 0 // 1: quality trimming of the untrimmed lengths issued ahead of the packing (measured: no gain)
-#endif
 #ifndef SPG_PRODUCER_SLEEP_NS
 #define SPG_PRODUCER_SLEEP_NS 1000
 #endif
@@ -178,12 +175,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem
 	             : "memory");
 }
 
-// lane 0 takes the next value of a shared-memory counter; predicated, so the warp does not diverge. Other lanes keep `keep`.
-__device__ __forceinline__ int claim_lane0(uint32_t counter, int lane, int keep)
-{
-	asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, 0;\n\t@p atom.shared.add.u32 %0, [%2], 1;\n\t}" : "+r"(keep) : "r"(lane), "r"(counter) : "memory");
-	return keep;
-}
 // 8-byte store by lane 0 only (predicated, no divergence)
 __device__ __forceinline__ void stg_v2_lane0(void* p, uint32_t x, uint32_t y, int lane)
 {
@@ -1257,15 +1248,8 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 	bool hasN1 = false, hasN2 = false;
 	Step123 st;
 	bool rare = true;
-	int spec_q1 = -1, spec_q2 = -1; // FULL variants: new lengths by quality trimming if both reads keep all FULL bases (-1: not known)
 	if (NW > 0 && FULL > 0 && P.len1 == FULL && P.len2 == FULL && !A.force_bytewise) // the host picks FULL variants only with A.full_ok
 	{
-		// quality trimming of the untrimmed reads, issued ahead of time: most pairs keep their length through steps 1-3, and the chain
-		// load -> shuffles -> votes -> decode has nothing else to overlap with at the end of the pair (no branches: it merges with the
-		// packing below into one stretch of code)
-#if SPG_SPEC_QUALITY
-		trim_quality_pair_core<true>(A, P, FULL, FULL, lane, spec_q1, spec_q2);
-#endif
 		Planes<NWP> f1, f2r;
 		const uint32_t bad = pack_full<NWP, FULLP, 0>(T, P.r1, lane, f1) | pack_full<NWP, FULLP, 32 * NWP - FULLP>(T, P.r2, lane, f2r);
 		bool not_plain;
@@ -1326,12 +1310,7 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 		if (A.qcut > 0) // :430-434
 		{
 			int t1, t2;
-			if (FULL > 0 && n1 == FULL && n2 == FULL && spec_q1 >= 0 && spec_q2 >= 0 && A.qwin <= 8)
-			{
-				t1 = spec_q1;
-				t2 = spec_q2;
-			}
-			else trim_quality_pair(A, P, n1, n2, lane, t1, t2);
+			trim_quality_pair(A, P, n1, n2, lane, t1, t2);
 			if (t1 < n1) flags |= SPG_F_Q1;
 			if (t2 < n2) flags |= SPG_F_Q2;
 			n1 = t1;
@@ -1372,8 +1351,7 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 
 // ---- the kernel: persistent CTAs, one producer warp + CW consumer warps, NS-stage TMA ring ------------------------------------------------------
 // dynamic shared memory: [stages][ b1 | q1 | b2 | q2 : tile_pairs*stride each ][ len1 | len2 : tile_pairs u16 each ]
-// Within a tile the consumer warps claim pairs one at a time from a shared counter, so that a warp that drew cheap pairs
-// (insert hit: no adapter scans) takes more of them and all warps release the stage at about the same time.
+// The pairs of a tile are dealt to the consumer warps round robin (pair index = warp, warp + CW, ...).
 // FULL > 0: additionally compiled for pairs of two reads of exactly FULL bases (the fast path above); 0: general code only.
 template <int NW, int CW, int MINB, int FULL = 0>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_constant__ KArgs A)
@@ -1383,7 +1361,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t full_bar[kMaxStages];
 	__shared__ __align__(8) uint64_t empty_bar[kMaxStages];
-	__shared__ int next_pair[kMaxStages];
 	__shared__ SmemTables T;
 	__shared__ FullTab<(NW > 0 ? NW : 1), (FULL > 0 ? FULL : 1)> F;
 
@@ -1396,12 +1373,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 	const uint32_t n_pairs = A.n_dev ? (uint32_t)*A.n_dev : (uint32_t)A.n_pairs;
 	const uint32_t n_tiles = (n_pairs + (uint32_t)TP - 1u) / (uint32_t)TP;
 	const uint32_t smem_base = smem_u32(smem);
-#if SPG_STATIC_PAIRS == 2
-	const int dealt = TP / CW > 1 ? TP / CW - 1 : 0; // pairs per warp and tile that are dealt round robin; the rest of the tile is claimed
-#else
-	const int dealt = 0;
-#endif
-	const int first_claimed = dealt * CW;
 
 	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads) T.mmin[i] = A.mmin[i];
 	for (int i = threadIdx.x; i < 256; i += kThreads) T.not_acgt[i] = (i == 'A' || i == 'C' || i == 'G' || i == 'T') ? 0 : 1;
@@ -1418,7 +1389,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 		{
 			mbar_init(&full_bar[s], 1);
 			mbar_init(&empty_bar[s], CW);
-			next_pair[s] = first_claimed;
 		}
 		fence_barrier_init();
 	}
@@ -1442,7 +1412,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 				if (round > 0)
 				{
 					mbar_wait_relaxed(&empty_bar[s], (round - 1) & 1u, SPG_PRODUCER_SLEEP_NS);
-					next_pair[s] = first_claimed; // published to the consumers by the release of the arrive below
 				}
 				const uint32_t first = t * (uint32_t)TP;
 				const int cnt = (int)min((uint32_t)TP, n_pairs - first);
@@ -1475,39 +1444,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 			const int cnt = (int)min((uint32_t)TP, n_pairs - first);
 			const uint32_t st = smem_base + (uint32_t)s * stage_bytes;
 			const uint32_t lens = st + 4 * plane_bytes;
-#if SPG_STATIC_PAIRS == 2
-			// Most pairs of a tile are dealt to the consumer warps round robin (no claim, no atomics); the last TP - dealt*CW pairs are
-			// claimed from a shared counter by whichever warp gets there first, which evens out the differences between the warps once
-			// per tile -- without it the spread between the warps of a CTA grows until the fastest ones wait at the ring all the time.
-			const uint32_t counter = smem_u32(&next_pair[s]);
-			for (int i = 0;;)
-			{
-				int pr;
-				if (i < dealt)
-				{
-					pr = warp + CW * i;
-					++i;
-					if (pr >= cnt) // ragged last tile
-					{
-						i = dealt;
-						continue;
-					}
-				}
-				else
-				{
-					pr = __shfl_sync(kFull, claim_lane0(counter, lane, 0), 0);
-					if (pr >= cnt) break;
-				}
-				const uint32_t roff = (uint32_t)pr * (uint32_t)A.stride;
-				Pair P;
-				P.r1 = st + roff;
-				P.q1 = P.r1 + plane_bytes;
-				P.r2 = P.r1 + 2 * plane_bytes;
-				P.q2 = P.r1 + 3 * plane_bytes;
-				P.len1 = (int)lds_u16(lens + 2u * (uint32_t)pr);
-				P.len2 = (int)lds_u16(lens + 2u * (uint32_t)(TP + pr));
-				spg_result* const outp = A.out + (first + (uint32_t)pr);
-#elif SPG_STATIC_PAIRS == 1
 			// pairs of a tile are dealt to the consumer warps round robin: no claim, the row addresses advance by additions. The ring
 			// buffers one tile of imbalance between the warps (a warp that is done moves on to the next stage on its own).
 			// (only the pair index is carried through the loop; everything else is derived from it and from per-tile values)
@@ -1521,27 +1457,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 				P.len1 = (int)lds_u16(lens + 2u * (uint32_t)pr);
 				P.len2 = (int)lds_u16(lens + 2u * (uint32_t)(TP + pr));
 				spg_result* const outp = A.out + (first + (uint32_t)pr);
-#else
-			// lane 0 claims pairs from the tile's counter; the claim for the NEXT pair is issued before the current pair is processed, so
-			// the latency of the shared-memory atomic and of the broadcast is hidden behind a whole pair of work (every warp over-claims
-			// once per tile, which is harmless: the producer resets the counter after all warps have left the stage)
-			const uint32_t counter = smem_u32(&next_pair[s]);
-			int raw = claim_lane0(counter, lane, 0x7fffffff);
-			for (;;)
-			{
-				const int pr = __reduce_min_sync(kFull, raw); // broadcast of lane 0's claim
-				if (pr >= cnt) break;
-				raw = claim_lane0(counter, lane, raw);
-				const uint32_t roff = (uint32_t)pr * (uint32_t)A.stride;
-				Pair P;
-				P.r1 = st + roff;
-				P.q1 = st + plane_bytes + roff;
-				P.r2 = st + 2 * plane_bytes + roff;
-				P.q2 = st + 3 * plane_bytes + roff;
-				P.len1 = (int)lds_u16(lens + 2u * (uint32_t)pr);
-				P.len2 = (int)lds_u16(lens + 2u * (uint32_t)(TP + pr));
-				spg_result* const outp = A.out + (first + (uint32_t)pr);
-#endif
 				bool edited = false;
 				process_pair<NW, FULL>(A, T, F, P, lane, outp, edited);
 				if (edited) // -ec: write the edited rows back

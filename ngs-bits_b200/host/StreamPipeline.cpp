@@ -407,6 +407,9 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 			fq_max_len = cfg.max_len;
 			fq_text_cap = cfg.text_cap;
 			next_slot = 0;
+			// the reads of a run share one length: the kernel variant compiled for it is picked from the first chunk on (a hint only,
+			// results do not depend on it)
+			spg_set_option(engine, SPG_OPT_FULL_LEN, need_len);
 		}
 		if ((int)in_flight.size() == n_slots) retire();
 		const int slot = next_slot;
