@@ -209,7 +209,7 @@ struct Device
 	unsigned long long* d_ec = nullptr; // 3 * SPG_MAXLEN
 	unsigned long long* d_qc = nullptr; // spg::kQcWords accumulators of the -qc statistics
 	int occ[4][3] = {};                 // resident CTAs per SM for NW = 0,5,8,10 x kernel variant (min blocks 2,3,4)
-	int full_occ[4][5] = {};            // same for the variants compiled for one read length (full_index)
+	int full_occ[4][9] = {};            // same for the variants compiled for one read length (full_index)
 	int qc_occ[3] = {};                 // same for qc_kernel, NW = 5,8,10
 };
 
@@ -339,9 +339,13 @@ cudaError_t launch_nw(const spg::KArgs& a, int minb, int sm_count, int ctas_per_
 // lengths of Illumina runs. Any other length runs the general kernel; results do not depend on the choice.
 int full_index(int nw, int full_len)
 {
-	if (nw == 5) return full_len == 150 ? 1 : full_len == 151 ? 2 : full_len == 100 ? 3 : full_len == 101 ? 4 : 0;
-	if (nw == 8) return full_len == 250 ? 1 : full_len == 251 ? 2 : 0;
-	if (nw == 10) return full_len == 300 ? 1 : full_len == 301 ? 2 : 0;
+	static const int lens5[] = {150, 151, 100, 101, 125, 126, 75, 76};
+	static const int lens8[] = {250, 251, 200, 201};
+	static const int lens10[] = {300, 301};
+	const int* tab = nw == 5 ? lens5 : nw == 8 ? lens8 : nw == 10 ? lens10 : nullptr;
+	const int n = nw == 5 ? 8 : nw == 8 ? 4 : nw == 10 ? 2 : 0;
+	for (int i = 0; i < n; ++i)
+		if (tab[i] == full_len) return i + 1;
 	return 0;
 }
 
@@ -435,15 +439,21 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	{
 		int* focc = &d.full_occ[nw_index(nw)][fi];
 #define SPG_FULL(NW_, FL_) e = launch_cfg<NW_, SPG_FULL_MINB, FL_>(a, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, focc)
-		switch (nw * 8 + fi)
+		switch (nw * 16 + fi)
 		{
-			case 5 * 8 + 1: SPG_FULL(5, 150); break;
-			case 5 * 8 + 2: SPG_FULL(5, 151); break;
-			case 5 * 8 + 3: SPG_FULL(5, 100); break;
-			case 5 * 8 + 4: SPG_FULL(5, 101); break;
-			case 8 * 8 + 1: SPG_FULL(8, 250); break;
-			case 8 * 8 + 2: SPG_FULL(8, 251); break;
-			case 10 * 8 + 1: SPG_FULL(10, 300); break;
+			case 5 * 16 + 1: SPG_FULL(5, 150); break;
+			case 5 * 16 + 2: SPG_FULL(5, 151); break;
+			case 5 * 16 + 3: SPG_FULL(5, 100); break;
+			case 5 * 16 + 4: SPG_FULL(5, 101); break;
+			case 5 * 16 + 5: SPG_FULL(5, 125); break;
+			case 5 * 16 + 6: SPG_FULL(5, 126); break;
+			case 5 * 16 + 7: SPG_FULL(5, 75); break;
+			case 5 * 16 + 8: SPG_FULL(5, 76); break;
+			case 8 * 16 + 1: SPG_FULL(8, 250); break;
+			case 8 * 16 + 2: SPG_FULL(8, 251); break;
+			case 8 * 16 + 3: SPG_FULL(8, 200); break;
+			case 8 * 16 + 4: SPG_FULL(8, 201); break;
+			case 10 * 16 + 1: SPG_FULL(10, 300); break;
 			default: SPG_FULL(10, 301); break;
 		}
 #undef SPG_FULL

@@ -377,7 +377,7 @@ def test_parameter_corners(sp, params):
     assert_same(got2, want, batch)
 
 
-FULL_LENGTHS = [150, 151, 100, 101, 250, 251, 300, 301]
+FULL_LENGTHS = [150, 151, 100, 101, 125, 126, 75, 76, 250, 251, 200, 201, 300, 301]
 
 
 def _full_batch(L, seed, n=1536):
