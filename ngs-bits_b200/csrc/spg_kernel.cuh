@@ -28,10 +28,6 @@
 #include "../../include/seqpurge_b200.h"
 
 
-#ifndef SPG_PRODUCER_SLEEP_NS
-#define SPG_PRODUCER_SLEEP_NS 1000
-#endif
-
 namespace spg
 {
 
@@ -149,24 +145,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 		    : "r"(smem_u32(bar)), "r"(parity), "r"(1000000u)
 		    : "memory");
 	} while (!ok);
-}
-// the producer's wait for a stage to be handed back: it has most of a tile's processing time to react, so it polls with real sleeps in
-// between instead of taking issue slots from the consumer warps (try_wait alone came back about 170 times per tile)
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns)
-{
-	for (;;)
-	{
-		uint32_t ok;
-		asm volatile(
-		    "{\n\t.reg .pred p;\n\t"
-		    "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-		    "selp.u32 %0, 1, 0, p;\n\t}"
-		    : "=r"(ok)
-		    : "r"(smem_u32(bar)), "r"(parity)
-		    : "memory");
-		if (ok) break;
-		__nanosleep(sleep_ns);
-	}
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
@@ -1411,7 +1389,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_
 				const uint32_t round = (uint32_t)(it / A.stages);
 				if (round > 0)
 				{
-					mbar_wait_relaxed(&empty_bar[s], (round - 1) & 1u, SPG_PRODUCER_SLEEP_NS);
+					mbar_wait(&empty_bar[s], (round - 1) & 1u);
 				}
 				const uint32_t first = t * (uint32_t)TP;
 				const int cnt = (int)min((uint32_t)TP, n_pairs - first);
