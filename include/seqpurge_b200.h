@@ -122,7 +122,9 @@ typedef struct spg_ctx spg_ctx;
    Builds the decision tables (match-probability ranks etc.) with the host's libm exactly as
    BasicStatistics::matchProbability does, uploads them to every device, allocates n_slots pinned host slots and the
    matching device buffers. Slot s runs on device_ids[s % n_devices] (host-side round robin, no collective).
-   max_len: longest read the caller will submit (<= 999). n_slots may be 0 (only spg_trim_device is used). */
+   max_len: longest read the caller will submit (<= 999); when it is one of the usual read lengths (75, 76, 100, 101, 125, 126, 150,
+   151, 200, 201, 250, 251, 300, 301) the kernel variant compiled for that length runs (a fast path for full-length pairs; the results
+   do not depend on it, see SPG_OPT_FULL_LEN). n_slots may be 0 (only spg_trim_device is used). */
 int spg_create(spg_ctx** ctx, const spg_params* params, const int* device_ids, int n_devices, int n_slots, int max_pairs, int max_len);
 
 /* Replaces: AnalysisJob storage (Auxilary.h:37-39). Pointers stay valid until spg_destroy. */
