@@ -436,6 +436,7 @@ int main(int argc, char** argv)
 				{
 					while (!in_flight.empty()) retire(); // drain before the slots are re-created for longer reads
 					createEngine(std::min(MAXLEN - 1, std::max((need + 15) / 16 * 16, 160)));
+					spg_set_option(engine, SPG_OPT_FULL_LEN, need); // the run's read length: picks the kernel variant compiled for it (a hint only)
 				}
 				workers[(size_t)j].reset(new GpuAnalysisWorker(job, params, stats, ec_stats, engine, j));
 				workers[(size_t)j]->start();
