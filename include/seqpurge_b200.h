@@ -62,7 +62,9 @@ typedef struct spg_params
 	int32_t qoff;        /* -qoff 33 */
 	int32_t ncut;        /* -ncut 7 (0 disables) */
 	int32_t ec;          /* -ec: error-correct insert-hit pairs; edited rows are returned in the slot */
-	int32_t qc;          /* -qc: also accumulate the raw-read statistics of every submitted batch (spg_qc_stats_get) */
+	int32_t qc;          /* -qc: also accumulate the raw-read statistics of every submitted batch (spg_qc_stats_get). 2: with the checks of
+	                        FastqEntry::validate as ReadQC runs them (src/cppNGS/FastqFileStream.cpp:3-48): bases of exactly A,C,G,T,N and
+	                        qualities of '!'..'J' (33..74), anything else counts in spg_qc_stats.errors */
 } spg_params;
 
 /* Per-pair output: everything OutputWorker / FastqWriter / TrimmingStatistics need (OutputWorker.cpp:36-77). 8 bytes. */
@@ -180,6 +182,10 @@ typedef struct spg_fq_config
 	int64_t text_cap;  /* bytes of text per file and chunk */
 	int32_t min_len;   /* -min_len: reads shorter than this after trimming are dropped (OutputWorker.cpp:41-56) */
 	int32_t singles;   /* 1: -out3 given, reads whose mate was dropped go to out[2] (read 1) / out[3] (read 2) */
+	int32_t stats_only; /* 1: framing and the -qc statistics only (the ReadQC tool, src/ReadQC/main.cpp:58-101): no trimming, no output text;
+	                       spg_fq_output carries the pair count, the consumed bytes, the lengths and the framing status */
+	int32_t single_end; /* 1 (with stats_only): only text1 is given; every record is one forward read, nothing is counted as reverse read */
+	int32_t validate;   /* 1: records are checked like FastqEntry::validate does (header starts with '@', header2 with '+', equal lengths) */
 } spg_fq_config;
 
 typedef struct spg_fq_input
@@ -194,6 +200,8 @@ typedef struct spg_fq_input
 #define SPG_FQ_HEADER_MISMATCH 1 /* "Headers of reads do not match" (AnalysisWorker.cpp:110-120) */
 #define SPG_FQ_LENGTH_MISMATCH 2 /* |bases| != |qualities| */
 #define SPG_FQ_TOO_LONG 3        /* read longer than max_len of this stream (or >= 1000) */
+#define SPG_FQ_BAD_HEADER 4      /* validate: "First header line does not start with '@'" (FastqFileStream.cpp:7-10) */
+#define SPG_FQ_BAD_HEADER2 5     /* validate: "Second header line does not start with '+'" (FastqFileStream.cpp:11-14) */
 
 typedef struct spg_fq_output
 {
@@ -208,6 +216,7 @@ typedef struct spg_fq_output
 	const uint8_t* frame_status; /* [n_pairs] SPG_FQ_* */
 	int32_t error_pair;          /* first pair with frame_status != 0 or results[].status != 0, or -1 */
 	int32_t max_len;             /* longest bases/qualities line of the chunk */
+	int32_t invalid_chars;       /* stats_only: != 0 if the chunk holds a base or quality that counts in spg_qc_stats.errors */
 } spg_fq_output;
 
 /* Attaches a FASTQ stream to a context (which provides parameters, tables, devices; it may have been created with n_slots = 0). */

@@ -497,10 +497,13 @@ cudaError_t launch_qc_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, int
 }
 
 int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, const uint8_t* b2, const uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride,
-              long long n, cudaStream_t stream, const int* n_dev = nullptr)
+              long long n, cudaStream_t stream, const int* n_dev = nullptr, bool forward_only = false, int* bad_flag = nullptr)
 {
 	if (n <= 0) return SPG_OK;
 	spg::QcArgs a;
+	a.bad_flag = bad_flag;
+	a.forward_only = forward_only ? 1 : 0;
+	a.strict = ctx->params.qc == 2 ? 1 : 0;
 	a.n_dev = n_dev;
 	a.b1 = b1;
 	a.q1 = q1;

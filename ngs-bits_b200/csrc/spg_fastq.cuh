@@ -34,7 +34,9 @@ enum : uint8_t
 	FQ_OK = 0,
 	FQ_HEADER_MISMATCH = 1, // AnalysisWorker.cpp:110-120
 	FQ_LENGTH_MISMATCH = 2, // |bases| != |qualities|
-	FQ_TOO_LONG = 3         // longer than the row stride of this engine (or >= MAXLEN)
+	FQ_TOO_LONG = 3,        // longer than the row stride of this engine (or >= MAXLEN)
+	FQ_BAD_HEADER = 4,      // validate: header does not start with '@'
+	FQ_BAD_HEADER2 = 5      // validate: header2 does not start with '+'
 };
 
 struct FqRec // where the two header lines of a record are in the text
@@ -80,6 +82,8 @@ struct FqArgs
 	int min_len;
 	int singles;      // -out3 given
 	unsigned long long* acons; // [2][40][5] A,C,G,T,N
+	int single_end;   // only text 0 holds records (ReadQC without -in2): read 2 of every pair is empty
+	int validate;     // FastqEntry::validate checks on the header lines
 };
 
 __device__ __forceinline__ uint32_t fq_newline_flags(uint32_t w) // bit 7 of every byte that equals '\n' (exact, no borrow artefacts)
@@ -245,13 +249,14 @@ __global__ void fq_plan(const __grid_constant__ FqArgs A)
 		rec[f] = A.final_[f] ? (lines + 3) / 4 : lines / 4;
 		P.records[f] = rec[f];
 	}
-	int n = min(min(rec[0], rec[1]), A.max_pairs);
+	int n = min(A.single_end ? rec[0] : min(rec[0], rec[1]), A.max_pairs);
 	P.n_pairs = n;
 	for (int f = 0; f < 2; ++f)
 	{
 		const long long last_line = 4ll * n - 1; // its end closes the n-th record
 		uint32_t c;
 		if (n == 0) c = 0;
+		else if (f == 1 && A.single_end) c = 0;
 		else if (last_line < P.lines[f]) c = min(A.nl[f][last_line] + 1u, A.bytes[f]);
 		else c = A.bytes[f]; // the final, incomplete record
 		P.consumed[f] = c;
@@ -310,6 +315,17 @@ __global__ void __launch_bounds__(256) fq_pack(const __grid_constant__ FqArgs A)
 		FqLine hdr[2];
 		for (int f = 0; f < 2; ++f)
 		{
+			if (f == 1 && A.single_end) // no mate: an empty read 2
+			{
+				if (lane == 0)
+				{
+					A.len[1][p] = 0;
+					FqRec r;
+					r.hs = r.hl = r.h2s = r.h2l = 0;
+					A.rec[1][p] = r;
+				}
+				continue;
+			}
 			const int lines = A.plan->lines[f];
 			const uint8_t* t = A.text[f];
 			hdr[f] = fq_line(A, f, 4 * p, lines);
@@ -319,6 +335,11 @@ __global__ void __launch_bounds__(256) fq_pack(const __grid_constant__ FqArgs A)
 			const uint32_t lb = b.e - b.s, lq = q.e - q.s;
 			max_len = max(max_len, (int)min(max(lb, lq), 0x7fffffffu));
 			uint32_t len = lb;
+			if (A.validate && st == FQ_OK) // FastqEntry::validate, in its order (FastqFileStream.cpp:7-18)
+			{
+				if (hdr[f].e == hdr[f].s || t[hdr[f].s] != '@') st = FQ_BAD_HEADER;
+				else if (h2.e == h2.s || t[h2.s] != '+') st = FQ_BAD_HEADER2;
+			}
 			if (lb != lq && st == FQ_OK) st = FQ_LENGTH_MISMATCH;
 			if ((lb > (uint32_t)A.stride || lq > (uint32_t)A.stride || lb >= (uint32_t)SPG_MAXLEN) && st == FQ_OK) st = FQ_TOO_LONG;
 			if (lb > (uint32_t)A.stride || lq > (uint32_t)A.stride || lb >= (uint32_t)SPG_MAXLEN || lb != lq) len = 0; // keeps the kernels behind inside the rows
@@ -340,7 +361,8 @@ __global__ void __launch_bounds__(256) fq_pack(const __grid_constant__ FqArgs A)
 				A.rec[f][p] = r;
 			}
 		}
-		// headers must match up to the first space, "/1" and "/2" aside (AnalysisWorker.cpp:110-120)
+		// headers must match up to the first space, "/1" and "/2" aside (AnalysisWorker.cpp:110-120); ReadQC does not compare them
+		if (!A.single_end && !A.validate)
 		{
 			const uint8_t* t1 = A.text[0];
 			const uint8_t* t2 = A.text[1];

@@ -40,6 +40,9 @@ struct QcArgs
 	int tile_pairs; // multiple of 8
 	int stages;     // <= kMaxStages
 	unsigned long long* acc; // [kQcWords]
+	int forward_only; // rows of read 2 are not read, nothing is counted as reverse read (single-end input)
+	int strict;       // FastqEntry::validate: bases of exactly A,C,G,T,N, qualities of 33..74 only
+	int* bad_flag;    // if not null: set to 1 when this launch met a character that counts in `errors` (per-chunk report of the FASTQ stream)
 };
 
 constexpr uint32_t kQcBad = 0x80000000u;
@@ -65,6 +68,14 @@ __device__ __forceinline__ uint32_t qc_qual_field(int byte)
 	return (uint32_t)q | (q >= 20 ? 0x1000u : 0u) | (q >= 30 ? 0x100000u : 0u);
 }
 
+// the additional checks of FastqEntry::validate (src/cppNGS/FastqFileStream.cpp:19-45, short reads)
+__device__ __forceinline__ bool qc_strict_bad(int strict, int byte, bool base)
+{
+	if (!strict) return false;
+	if (base) return !(byte == 'A' || byte == 'C' || byte == 'G' || byte == 'T' || byte == 'N');
+	return byte < 33 || byte > 74;
+}
+
 template <int NW, int CW>
 __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant__ QcArgs A)
 {
@@ -88,8 +99,8 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 
 	for (int i = threadIdx.x; i < 256; i += kThreads)
 	{
-		lutb[i] = qc_base_field(i);
-		lutq[i] = qc_qual_field(i);
+		lutb[i] = qc_base_field(i) | (qc_strict_bad(A.strict, i, true) ? kQcBad : 0u);
+		lutq[i] = qc_qual_field(i) | (qc_strict_bad(A.strict, i, false) ? kQcBad : 0u);
 	}
 	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads) s_len[i] = 0;
 	for (int i = threadIdx.x; i < 7 * NW * 32; i += kThreads) (&s_acc[0][0])[i] = 0;
@@ -178,6 +189,7 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 #pragma unroll
 				for (int rd = 0; rd < 2; ++rd)
 				{
+					if (rd == 1 && A.forward_only) break;
 					const uint32_t rb = st + (uint32_t)(2 * rd) * plane_bytes + roff, rq = rb + plane_bytes;
 					int len = (int)lds_u16(lens + 2u * (uint32_t)(rd * TP + pr));
 					bases += (unsigned long long)len;
@@ -223,12 +235,13 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 		if (lane == 0)
 		{
 			atomicAdd(&s_scalar[kQcReadsF], (unsigned long long)reads);
-			atomicAdd(&s_scalar[kQcReadsR], (unsigned long long)reads);
+			if (!A.forward_only) atomicAdd(&s_scalar[kQcReadsR], (unsigned long long)reads);
 			atomicAdd(&s_scalar[kQcBases], bases);
 			atomicAdd(&s_scalar[kQcReadQ20], (unsigned long long)rq20);
 			atomicAdd(&s_scalar[kQcBaseQ20], t20);
 			atomicAdd(&s_scalar[kQcBaseQ30], t30);
 			if (any_bad) atomicAdd(&s_scalar[kQcErrors], 1ull);
+			if (any_bad && A.bad_flag) atomicMax(A.bad_flag, 1);
 		}
 	}
 	__syncthreads();
@@ -256,7 +269,7 @@ __global__ void __launch_bounds__(256) qc_kernel_generic(const __grid_constant__
 	const long long n_pairs = A.n_dev ? (long long)*A.n_dev : A.n_pairs;
 	for (long long r = gwarp; r < n_pairs; r += nwarps)
 	{
-		for (int rd = 0; rd < 2; ++rd)
+		for (int rd = 0; rd < (A.forward_only ? 1 : 2); ++rd)
 		{
 			const uint8_t* brow = (rd ? A.b2 : A.b1) + (size_t)r * A.stride;
 			const uint8_t* qrow = (rd ? A.q2 : A.q1) + (size_t)r * A.stride;
@@ -267,7 +280,7 @@ __global__ void __launch_bounds__(256) qc_kernel_generic(const __grid_constant__
 			for (int pos = lane; pos < len && !bad; pos += 32)
 			{
 				const uint32_t vb = qc_base_field(brow[pos]), vq = qc_qual_field(qrow[pos]);
-				if ((vb | vq) & kQcBad)
+				if (((vb | vq) & kQcBad) || qc_strict_bad(A.strict, brow[pos], true) || qc_strict_bad(A.strict, qrow[pos], false))
 				{
 					bad = true;
 					break;
@@ -292,6 +305,7 @@ __global__ void __launch_bounds__(256) qc_kernel_generic(const __grid_constant__
 				atomicAdd(&A.acc[kQcBaseQ20], (unsigned long long)t20);
 				atomicAdd(&A.acc[kQcBaseQ30], (unsigned long long)t30);
 				if (any_bad) atomicAdd(&A.acc[kQcErrors], 1ull);
+				if (any_bad && A.bad_flag) atomicMax(A.bad_flag, 1);
 			}
 		}
 	}

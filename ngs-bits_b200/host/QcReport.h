@@ -21,6 +21,7 @@ std::vector<std::pair<std::string, std::string>> qcMetrics(const spg_qc_stats& s
 // adds b into a (statistics of several engines / devices)
 void qcAccumulate(spg_qc_stats& a, const spg_qc_stats& b);
 
-void storeQcML(const std::string& filename, const spg_qc_stats& stats, const std::vector<std::string>& source_files, const std::string& parameters);
+void storeQcML(const std::string& filename, const spg_qc_stats& stats, const std::vector<std::string>& source_files, const std::string& parameters,
+               const std::string& software = "seqpurge_b200");
 
 } // namespace seqpurge

@@ -24,6 +24,7 @@
 #include "GpuAnalysisWorker.h"
 #include "GzipTextWriter.h"
 #include "QcReport.h"
+#include "ChunkReader.h"
 #include "TextSource.h"
 
 namespace seqpurge
@@ -31,154 +32,6 @@ namespace seqpurge
 
 namespace
 {
-
-struct TextChunk
-{
-	std::vector<uint8_t> data;
-	int records = 0;      // entries readEntry would deliver for this text (an unterminated last line and an incomplete last record count)
-	int max_read_len = 0; // longest bases/qualities line (may include trailing '\r')
-	bool file_end = false;
-	size_t file_index = 0;
-};
-
-class ChunkQueue
-{
-public:
-	explicit ChunkQueue(size_t depth) : depth_(depth) {}
-	void push(std::unique_ptr<TextChunk> c)
-	{
-		std::unique_lock<std::mutex> l(mu_);
-		cv_.wait(l, [this] { return q_.size() < depth_ || aborted_; });
-		if (aborted_) return;
-		q_.push_back(std::move(c));
-		cv_.notify_all();
-	}
-	std::unique_ptr<TextChunk> pop() // nullptr: the reader is done (or failed: see failure())
-	{
-		std::unique_lock<std::mutex> l(mu_);
-		cv_.wait(l, [this] { return !q_.empty() || done_ || aborted_; });
-		if (q_.empty()) return nullptr;
-		std::unique_ptr<TextChunk> c = std::move(q_.front());
-		q_.pop_front();
-		cv_.notify_all();
-		return c;
-	}
-	void finish(std::exception_ptr e)
-	{
-		std::lock_guard<std::mutex> g(mu_);
-		done_ = true;
-		failure_ = e;
-		cv_.notify_all();
-	}
-	void abort()
-	{
-		std::lock_guard<std::mutex> g(mu_);
-		aborted_ = true;
-		cv_.notify_all();
-	}
-	std::exception_ptr failure()
-	{
-		std::lock_guard<std::mutex> g(mu_);
-		return failure_;
-	}
-
-private:
-	size_t depth_;
-	std::mutex mu_;
-	std::condition_variable cv_;
-	std::deque<std::unique_ptr<TextChunk>> q_;
-	bool done_ = false, aborted_ = false;
-	std::exception_ptr failure_;
-};
-
-// reads the files of one list, cuts the inflated text after every `pairs` records
-void readerLoop(const std::vector<std::string>& files, int pairs, ChunkQueue& out, WorkerPool* pool)
-{
-	try
-	{
-		std::vector<uint8_t> buf((size_t)4 << 20);
-		for (size_t fi = 0; fi < files.size(); ++fi)
-		{
-			std::unique_ptr<TextSource> src = openTextSource(files[fi], pool); // BGZF inputs are inflated by the pool, anything else by gzFile
-			std::unique_ptr<TextChunk> cur(new TextChunk());
-			cur->file_index = fi;
-			long long lines = 0;   // complete lines in cur
-			size_t line_len = 0;   // bytes of the current (incomplete) line
-			const long long cut = 4ll * pairs;
-			for (;;)
-			{
-				const size_t n = src->read(buf.data(), buf.size());
-				if (n == 0) break;
-				const uint8_t* p = buf.data();
-				const uint8_t* end = p + n;
-				const uint8_t* start = p; // first byte not yet appended to cur
-				while (p < end)
-				{
-					const uint8_t* nl = (const uint8_t*)memchr(p, '\n', (size_t)(end - p));
-					if (!nl)
-					{
-						line_len += (size_t)(end - p);
-						break;
-					}
-					line_len += (size_t)(nl - p);
-					if (lines & 1) cur->max_read_len = (int)std::min<size_t>(std::max<size_t>((size_t)cur->max_read_len, line_len), 1u << 30);
-					line_len = 0;
-					++lines;
-					p = nl + 1;
-					if (lines == cut)
-					{
-						cur->data.insert(cur->data.end(), start, p);
-						cur->records = pairs;
-						out.push(std::move(cur));
-						cur.reset(new TextChunk());
-						cur->file_index = fi;
-						lines = 0;
-						start = p;
-					}
-				}
-				cur->data.insert(cur->data.end(), start, end);
-			}
-			src.reset();
-			if (line_len > 0) // unterminated last line
-			{
-				if (lines & 1) cur->max_read_len = (int)std::min<size_t>(std::max<size_t>((size_t)cur->max_read_len, line_len), 1u << 30);
-				++lines;
-			}
-			cur->records = (int)((lines + 3) / 4);
-			cur->file_end = true;
-			out.push(std::move(cur));
-		}
-		out.finish(nullptr);
-	}
-	catch (...)
-	{
-		out.finish(std::current_exception());
-	}
-}
-
-// the `index`-th record of a chunk as the reference's reader delivers it (error reporting only)
-FastqEntry entryAt(const TextChunk& c, int index)
-{
-	FastqEntry e;
-	const uint8_t* p = c.data.data();
-	const uint8_t* end = p + c.data.size();
-	std::string* field[4] = {&e.header, &e.bases, &e.header2, &e.qualities};
-	long long line = 0;
-	while (p < end && line < 4ll * index + 4)
-	{
-		const uint8_t* nl = (const uint8_t*)memchr(p, '\n', (size_t)(end - p));
-		const uint8_t* le = nl ? nl : end;
-		if (line >= 4ll * index)
-		{
-			const uint8_t* e2 = le;
-			while (e2 > p && e2[-1] == '\r') --e2;
-			field[line - 4ll * index]->assign((const char*)p, (size_t)(e2 - p));
-		}
-		++line;
-		p = nl ? nl + 1 : end;
-	}
-	return e;
-}
 
 bool endsWith(const std::string& s, const char* suffix)
 {
@@ -395,6 +248,7 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 			while (!in_flight.empty()) retire();
 			closeStream();
 			spg_fq_config cfg;
+			memset(&cfg, 0, sizeof(cfg));
 			cfg.n_slots = n_slots;
 			cfg.max_pairs = pairs;
 			cfg.max_len = std::min(MAXLEN - 1, std::max(std::max((need_len + 15) / 16 * 16, fq_max_len), 160));

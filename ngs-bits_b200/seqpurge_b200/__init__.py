@@ -129,7 +129,7 @@ class TrimmingParameters:
     qoff: int = 33
     ncut: int = 7
     ec: bool = False
-    qc: bool = False
+    qc: int = 0  # 1: also accumulate the read statistics; 2: with the character checks of FastqEntry::validate (ReadQC)
 
     def _c(self):
         a1, a2 = self.a1.encode(), self.a2.encode()
@@ -180,7 +180,8 @@ class Slot:
 
 
 class _FqConfig(C.Structure):
-    _fields_ = [("n_slots", C.c_int32), ("max_pairs", C.c_int32), ("max_len", C.c_int32), ("text_cap", C.c_int64), ("min_len", C.c_int32), ("singles", C.c_int32)]
+    _fields_ = [("n_slots", C.c_int32), ("max_pairs", C.c_int32), ("max_len", C.c_int32), ("text_cap", C.c_int64), ("min_len", C.c_int32), ("singles", C.c_int32),
+                ("stats_only", C.c_int32), ("single_end", C.c_int32), ("validate", C.c_int32)]
 
 
 class _FqInput(C.Structure):
@@ -190,7 +191,7 @@ class _FqInput(C.Structure):
 class _FqOutput(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("records1", C.c_int32), ("records2", C.c_int32), ("consumed1", C.c_int64), ("consumed2", C.c_int64),
                 ("out", C.c_void_p * 4), ("out_bytes", C.c_int64 * 4), ("results", C.c_void_p), ("len1", C.c_void_p), ("len2", C.c_void_p),
-                ("frame_status", C.c_void_p), ("error_pair", C.c_int32), ("max_len", C.c_int32)]
+                ("frame_status", C.c_void_p), ("error_pair", C.c_int32), ("max_len", C.c_int32), ("invalid_chars", C.c_int32)]
 
 
 _lib.spg_fq_open.argtypes = [C.c_void_p, C.POINTER(_FqConfig), C.POINTER(C.c_void_p)]
@@ -309,20 +310,22 @@ class FastqChunk:
         n = o.n_pairs
         self.n_pairs, self.records, self.consumed = n, (o.records1, o.records2), (o.consumed1, o.consumed2)
         self.out = [C.string_at(o.out[k], o.out_bytes[k]) if o.out_bytes[k] else b"" for k in range(4)]
-        self.results = _np_view(o.results, (n,), RESULT_DTYPE).copy() if n else np.zeros(0, RESULT_DTYPE)
+        self.results = _np_view(o.results, (n,), RESULT_DTYPE).copy() if n and o.results else np.zeros(0, RESULT_DTYPE)
         self.len1 = _np_view(o.len1, (n,), np.uint16).copy() if n else np.zeros(0, np.uint16)
         self.len2 = _np_view(o.len2, (n,), np.uint16).copy() if n else np.zeros(0, np.uint16)
         self.frame_status = _np_view(o.frame_status, (n,), np.uint8).copy() if n else np.zeros(0, np.uint8)
-        self.error_pair, self.max_len = o.error_pair, o.max_len
+        self.error_pair, self.max_len, self.invalid_chars = o.error_pair, o.max_len, o.invalid_chars
 
 
 class FastqStream:
     """FASTQ text in, FASTQ text out on the device (spg_fq_*): framing, trimming, routing by min_len, record layout."""
 
-    def __init__(self, engine, n_slots=2, max_pairs=65536, max_len=160, text_cap=32 << 20, min_len=30, singles=False):
+    def __init__(self, engine, n_slots=2, max_pairs=65536, max_len=160, text_cap=32 << 20, min_len=30, singles=False, stats_only=False, single_end=False,
+                 validate=False):
+        """stats_only / single_end / validate: the ReadQC form of the stream (framing and read statistics only, see spg_fq_config)."""
         self.engine = engine
         self._h = C.c_void_p()
-        cfg = _FqConfig(n_slots, max_pairs, max_len, text_cap, min_len, int(singles))
+        cfg = _FqConfig(n_slots, max_pairs, max_len, text_cap, min_len, int(singles), int(stats_only), int(single_end), int(validate))
         engine._check(_lib.spg_fq_open(engine._h, C.byref(cfg), C.byref(self._h)), "spg_fq_open")
         self.text_cap, self.n_slots = text_cap, n_slots
 

@@ -65,7 +65,11 @@ def qc_metrics(d):
     bases_total = int(pile.sum())
     keys = [int(i) for i in np.nonzero(d["read_lengths"])[0]]
     lengths = ", ".join(str(k) for k in keys) if len(keys) < 4 else f"{keys[0]}-{keys[-1]}"
-    f2 = lambda v: f"{v:.2f}"  # noqa: E731
+    def f2(v):  # QString::number(v, 'f', 2): an exact tie goes up (double-conversion), not to even like printf -- 0.125 -> "0.13"
+        from decimal import ROUND_HALF_UP, Decimal
+
+        return str(Decimal(float(v)).quantize(Decimal("0.01"), rounding=ROUND_HALF_UP))
+
     return [
         ("read count", str(total_reads)),
         ("read length", lengths),
