@@ -186,7 +186,13 @@ typedef struct spg_fq_config
 	                       spg_fq_output carries the pair count, the consumed bytes, the lengths and the framing status */
 	int32_t single_end; /* 1 (with stats_only): only text1 is given; every record is one forward read, nothing is counted as reverse read */
 	int32_t validate;   /* 1: records are checked like FastqEntry::validate does (header starts with '@', header2 with '+', equal lengths) */
+	int32_t fixed_trim; /* 1 (with single_end): the FastqTrim tool (src/FastqTrim/main.cpp:47-77) instead of SeqPurge's trimming: every read of
+	                       text1 loses trim_start bases at its start and trim_end at its end (reads of at most trim_start+trim_end bases are
+	                       dropped), is then cut to trim_len bases (0 = no limit); reads of trim_max_len bases and more (0 = off) pass
+	                       unchanged. Output text in out[0]; results[].len1 = new length, best_offset = first base kept, flags 0x80 = dropped */
+	int32_t trim_start, trim_end, trim_len, trim_max_len;
 } spg_fq_config;
+#define SPG_F_DROPPED 0x80u /* fixed_trim: the read is not written */
 
 typedef struct spg_fq_input
 {

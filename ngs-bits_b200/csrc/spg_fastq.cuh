@@ -84,6 +84,9 @@ struct FqArgs
 	unsigned long long* acons; // [2][40][5] A,C,G,T,N
 	int single_end;   // only text 0 holds records (ReadQC without -in2): read 2 of every pair is empty
 	int validate;     // FastqEntry::validate checks on the header lines
+	int fixed_trim;   // FastqTrim (src/FastqTrim/main.cpp:47-77) on the reads of text 0
+	int ft_start, ft_end, ft_len, ft_max_len;
+	spg_result* res_w; // fixed_trim: the records this mode writes itself (same buffer as res)
 };
 
 __device__ __forceinline__ uint32_t fq_newline_flags(uint32_t w) // bit 7 of every byte that equals '\n' (exact, no borrow artefacts)
@@ -393,6 +396,39 @@ __global__ void __launch_bounds__(256) fq_pack(const __grid_constant__ FqArgs A)
 	if (lane == 0 && max_len > 0) atomicMax(&A.plan->max_len, max_len);
 }
 
+// FastqTrim (src/FastqTrim/main.cpp:47-77): one thread per read; len1 = bases kept, best_offset = first base kept, SPG_F_DROPPED if the
+// read is not written
+__global__ void __launch_bounds__(256) fq_fixed_trim(const __grid_constant__ FqArgs A)
+{
+	const int n = A.plan->n_pairs;
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+	{
+		const int len = A.len[0][p];
+		int off = 0, keep_n = len;
+		bool keep = true;
+		if (!(A.ft_max_len > 0 && len >= A.ft_max_len)) // reads of max_len bases and more pass unchanged (:52-56)
+		{
+			if (A.ft_start > 0 || A.ft_end > 0) // :58-64
+			{
+				if (len <= A.ft_start + A.ft_end) keep = false;
+				else
+				{
+					off = A.ft_start;
+					keep_n = len - A.ft_start - A.ft_end;
+				}
+			}
+			if (keep && A.ft_len > 0 && keep_n > A.ft_len) keep_n = A.ft_len; // :66-70
+		}
+		spg_result r;
+		r.len1 = (uint16_t)(keep ? keep_n : 0);
+		r.len2 = 0;
+		r.best_offset = (int16_t)off;
+		r.flags = keep ? 0 : (uint8_t)SPG_F_DROPPED;
+		r.status = 0;
+		A.res_w[p] = r;
+	}
+}
+
 // ---- output --------------------------------------------------------------------------------------------------------------------------------
 // bytes a pair contributes to the four streams
 __device__ __forceinline__ void fq_pair_sizes(const FqArgs& A, int p, uint32_t sz[4], int& l1, int& l2)
@@ -400,6 +436,13 @@ __device__ __forceinline__ void fq_pair_sizes(const FqArgs& A, int p, uint32_t s
 	const spg_result r = A.res[p];
 	l1 = r.len1;
 	l2 = r.len2;
+	if (A.fixed_trim) // one stream, every read that was not dropped
+	{
+		const FqRec a = A.rec[0][p];
+		sz[0] = (r.flags & SPG_F_DROPPED) ? 0u : a.hl + a.h2l + 2u * (uint32_t)l1 + 4u;
+		sz[1] = sz[2] = sz[3] = 0;
+		return;
+	}
 	const bool ok1 = l1 >= A.min_len, ok2 = l2 >= A.min_len;
 	const FqRec a = A.rec[0][p], b = A.rec[1][p];
 	const uint32_t s1 = a.hl + a.h2l + 2u * (uint32_t)l1 + 4u;
@@ -566,6 +609,11 @@ __global__ void __launch_bounds__(kFqOutPairs) fq_out_write(const __grid_constan
 		const uint8_t* q1 = A.rows[1] + (size_t)p * A.stride;
 		const uint8_t* b2 = A.rows[2] + (size_t)p * A.stride;
 		const uint8_t* q2 = A.rows[3] + (size_t)p * A.stride;
+		if (A.fixed_trim)
+		{
+			if (!(r.flags & SPG_F_DROPPED)) fq_write_record(A.out[0] + offs[0][j], A.text[0], A.rec[0][p], b1 + r.best_offset, q1 + r.best_offset, (uint32_t)l1, lane);
+			continue;
+		}
 		if (ok1 && ok2)
 		{
 			fq_write_record(A.out[0] + offs[0][j], A.text[0], A.rec[0][p], b1, q1, (uint32_t)l1, lane);

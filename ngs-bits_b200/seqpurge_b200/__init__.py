@@ -181,7 +181,8 @@ class Slot:
 
 class _FqConfig(C.Structure):
     _fields_ = [("n_slots", C.c_int32), ("max_pairs", C.c_int32), ("max_len", C.c_int32), ("text_cap", C.c_int64), ("min_len", C.c_int32), ("singles", C.c_int32),
-                ("stats_only", C.c_int32), ("single_end", C.c_int32), ("validate", C.c_int32)]
+                ("stats_only", C.c_int32), ("single_end", C.c_int32), ("validate", C.c_int32), ("fixed_trim", C.c_int32),
+                ("trim_start", C.c_int32), ("trim_end", C.c_int32), ("trim_len", C.c_int32), ("trim_max_len", C.c_int32)]
 
 
 class _FqInput(C.Structure):
@@ -321,11 +322,12 @@ class FastqStream:
     """FASTQ text in, FASTQ text out on the device (spg_fq_*): framing, trimming, routing by min_len, record layout."""
 
     def __init__(self, engine, n_slots=2, max_pairs=65536, max_len=160, text_cap=32 << 20, min_len=30, singles=False, stats_only=False, single_end=False,
-                 validate=False):
+                 validate=False, fixed_trim=None):
         """stats_only / single_end / validate: the ReadQC form of the stream (framing and read statistics only, see spg_fq_config)."""
         self.engine = engine
         self._h = C.c_void_p()
-        cfg = _FqConfig(n_slots, max_pairs, max_len, text_cap, min_len, int(singles), int(stats_only), int(single_end), int(validate))
+        ft = fixed_trim or (0, 0, 0, 0)  # (start, end, len, max_len) of the FastqTrim form of the stream
+        cfg = _FqConfig(n_slots, max_pairs, max_len, text_cap, min_len, int(singles), int(stats_only), int(single_end), int(validate), int(fixed_trim is not None), *ft)
         engine._check(_lib.spg_fq_open(engine._h, C.byref(cfg), C.byref(self._h)), "spg_fq_open")
         self.text_cap, self.n_slots = text_cap, n_slots
 
