@@ -25,6 +25,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "../../include/seqpurge_b200.h"
 
 
@@ -77,6 +79,18 @@ struct KArgs
 	uint8_t a1[32];     // adapter bytes (first 32)
 	uint8_t a2[32];
 };
+
+// f(std::integral_constant<int, 0>{}), ..., f(std::integral_constant<int, N-1>{}): a loop whose index is a compile-time constant in the
+// body (offsets folded into instructions)
+template <int N, int I = 0, typename F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+	if constexpr (I < N)
+	{
+		f(std::integral_constant<int, I>{});
+		static_for<N, I + 1>(f);
+	}
+}
 
 // ---- PTX helpers: shared-window loads/stores, mbarrier, 1-D bulk copy (TMA) --------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -929,34 +943,19 @@ __device__ __forceinline__ uint32_t pack_full(const SmemTables& T, uint32_t row,
 	uint32_t bad = 0;
 	const uint32_t lut = smem_u32(T.not_acgt);
 	const uint32_t base = row + lane - D;
-#pragma unroll
-	for (int w = 0; w < NW; ++w)
-	{
-		const int lo = 32 * w - D, hi = 32 * w + 31 - D; // positions held by lanes 0 and 31
-		if (hi < 0 || lo >= FULL)
+	static_for<NW>([&](auto wc) {
+		constexpr int w = decltype(wc)::value;
+		constexpr int lo = 32 * w - D, hi = 32 * w + 31 - D; // positions held by lanes 0 and 31
+		if constexpr (hi < 0 || lo >= FULL) pl.h[w] = pl.l[w] = 0;
+		else
 		{
-			pl.h[w] = pl.l[w] = 0;
-			continue;
+			uint32_t c = lds_u8_at<32 * w>(base);
+			if constexpr (lo < 0 || hi >= FULL) c = ((unsigned)(32 * w + lane - D) < (unsigned)FULL) ? c : (uint32_t)'A';
+			pl.h[w] = ballot_bits(c, 4u);
+			pl.l[w] = ballot_bits(c, 2u);
+			bad |= lds_u8(lut + c);
 		}
-		uint32_t c;
-		switch (w)
-		{
-			case 0: c = lds_u8_at<0>(base); break;
-			case 1: c = lds_u8_at<32>(base); break;
-			case 2: c = lds_u8_at<64>(base); break;
-			case 3: c = lds_u8_at<96>(base); break;
-			case 4: c = lds_u8_at<128>(base); break;
-			case 5: c = lds_u8_at<160>(base); break;
-			case 6: c = lds_u8_at<192>(base); break;
-			case 7: c = lds_u8_at<224>(base); break;
-			case 8: c = lds_u8_at<256>(base); break;
-			default: c = lds_u8_at<288>(base); break;
-		}
-		if (lo < 0 || hi >= FULL) c = ((unsigned)(32 * w + lane - D) < (unsigned)FULL) ? c : (uint32_t)'A';
-		pl.h[w] = ballot_bits(c, 4u);
-		pl.l[w] = ballot_bits(c, 2u);
-		bad |= lds_u8(lut + c);
-	}
+	});
 	return bad;
 }
 
@@ -997,9 +996,8 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 		const uint32_t thr_addr = smem_u32(F.thr) + 2u * (uint32_t)lane;
 		int mmlq[NW];
 		bool any = false;
-#pragma unroll
-		for (int q = 0; q < NW; ++q)
-		{
+		static_for<NW>([&](auto qc) {
+			constexpr int q = decltype(qc)::value;
 			int mml = 0;
 #pragma unroll
 			for (int k = 0; k < NW - q; ++k)
@@ -1010,23 +1008,9 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 				else x = xor_and(s2l[w], f1.l[k], mk[w]);
 				mml += __popc(x);
 			}
-			int t;
-			switch (q)
-			{
-				case 0: t = lds_s16_at<0>(thr_addr); break;
-				case 1: t = lds_s16_at<64>(thr_addr); break;
-				case 2: t = lds_s16_at<128>(thr_addr); break;
-				case 3: t = lds_s16_at<192>(thr_addr); break;
-				case 4: t = lds_s16_at<256>(thr_addr); break;
-				case 5: t = lds_s16_at<320>(thr_addr); break;
-				case 6: t = lds_s16_at<384>(thr_addr); break;
-				case 7: t = lds_s16_at<448>(thr_addr); break;
-				case 8: t = lds_s16_at<512>(thr_addr); break;
-				default: t = lds_s16_at<576>(thr_addr); break;
-			}
 			mmlq[q] = mml;
-			any |= mml <= t;
-		}
+			any |= mml <= lds_s16_at<64 * q>(thr_addr); // the limit of offset 32*q+lane
+		});
 		if (__any_sync(kFull, any || (bad & 1u))) // pairs with an insert match, false survivors of the pre-filter, pairs with N etc.
 		{
 			if (__any_sync(kFull, bad & 1u))
@@ -1082,29 +1066,21 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 		shift_words<NW>(f1.h, lane, sh);
 		shift_words<NW>(f1.l, lane, sl);
 		const uint32_t tail_addr = smem_u32(F.r1tail) + 8u * (uint32_t)lane;
-#pragma unroll
-		for (int q = 0; q < NW; ++q)
-		{
+		static_for<NW>([&](auto qc) {
+			constexpr int q = decltype(qc)::value;
 			const uint32_t x = (sh[q] ^ A.a1h) | (sl[q] ^ A.a1l);
-			if (q < QF)
+			if constexpr (q < QF)
 			{
 				mm1[q] = __popc(x * a1mul);
 				any1 |= mm1[q] <= A.a1maxmm;
 			}
 			else
 			{
-				uint2 t;
-				switch (q - QF)
-				{
-					case 0: t = lds_v2_at<0>(tail_addr); break;
-					case 1: t = lds_v2_at<256>(tail_addr); break;
-					case 2: t = lds_v2_at<512>(tail_addr); break;
-					default: t = lds_v2_at<768>(tail_addr); break;
-				}
+				const uint2 t = lds_v2_at<256 * (q - QF)>(tail_addr); // F.r1tail[q - QF][lane]
 				mm1[q] = __popc(x * t.x);
 				any1 |= mm1[q] <= (int)t.y;
 			}
-		}
+		});
 	}
 	// ---- step 3: read 2 (original orientation, right-aligned planes) against adapter 2 ----
 	{
@@ -1112,37 +1088,26 @@ __device__ __forceinline__ Step123 steps_full(const KArgs& A, const FullTab<NW, 
 		shift_words<NW>(f2r.h, lane, sh);
 		shift_words<NW>(f2r.l, lane, sl);
 		const uint32_t lim_addr = smem_u32(F.r2lim) + 2u * (uint32_t)lane;
-#pragma unroll
-		for (int q = 0; q < NW; ++q)
-		{
-			const uint32_t x = (sh[q] ^ A.a2h) | (sl[q] ^ A.a2l);
-			if (32 * q + 31 < D) // the whole round lies in the padding in front of the read
-			{
-				mm2[q] = 0x7fff;
-				continue;
-			}
-			if (q < NW - 1)
-			{
-				mm2[q] = __popc(x * a1mul);
-				int lim = A.a2maxmm;
-				if (32 * q < D) // some lanes of this round start in the padding: per-lane limit
-				{
-					switch (q)
-					{
-						case 0: lim = lds_s16_at<0>(lim_addr); break;
-						case 1: lim = lds_s16_at<64>(lim_addr); break;
-						case 2: lim = lds_s16_at<128>(lim_addr); break;
-						default: lim = F.r2lim[q][lane]; break;
-					}
-				}
-				any2 |= mm2[q] <= lim;
-			}
+		static_for<NW>([&](auto qc) {
+			constexpr int q = decltype(qc)::value;
+			if constexpr (32 * q + 31 < D) mm2[q] = 0x7fff; // the whole round lies in the padding in front of the read
 			else
 			{
-				mm2[q] = __popc(x * (uint32_t)t2.x);
-				any2 |= mm2[q] <= t2.y;
+				const uint32_t x = (sh[q] ^ A.a2h) | (sl[q] ^ A.a2l);
+				if constexpr (q < NW - 1)
+				{
+					mm2[q] = __popc(x * a1mul);
+					int lim = A.a2maxmm;
+					if constexpr (32 * q < D) lim = lds_s16_at<64 * q>(lim_addr); // some lanes of this round start in the padding: F.r2lim[q][lane]
+					any2 |= mm2[q] <= lim;
+				}
+				else
+				{
+					mm2[q] = __popc(x * (uint32_t)t2.x);
+					any2 |= mm2[q] <= t2.y;
+				}
 			}
-		}
+		});
 	}
 	if (__any_sync(kFull, any1 || any2)) // one vote for both reads; the positions are worked out only for hits
 	{
@@ -1334,7 +1299,7 @@ __device__ __forceinline__ void process_pair(const KArgs& A, const SmemTables& T
 template <int NW, int CW, int MINB, int FULL = 0>
 __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_kernel(const __grid_constant__ KArgs A)
 {
-	static_assert(FULL == 0 || (NW > 0 && FULL <= 32 * NW && FULL >= 52 && NW - full_qf(FULL) <= 4), "FULL must fit the plane words");
+	static_assert(FULL == 0 || (NW > 0 && FULL <= 32 * NW && FULL >= 52), "FULL must fit the plane words");
 	constexpr int kThreads = (CW + 1) * 32;
 	extern __shared__ __align__(128) uint8_t smem[];
 	__shared__ __align__(8) uint64_t full_bar[kMaxStages];

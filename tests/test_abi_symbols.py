@@ -55,3 +55,23 @@ def test_struct_layouts_match_header():
     assert sp.RESULT_DTYPE.itemsize == 8
     assert ctypes.sizeof(sp._EcStats) == 3 * 1000 * 8
     assert ctypes.sizeof(sp._SlotView) == 6 * 8 + 8
+
+
+def test_ctypes_structs_have_the_sizes_the_compiler_gives_the_header(tmp_path):
+    """Every struct of include/seqpurge_b200.h that the Python binding mirrors: sizeof from gcc == ctypes.sizeof (guards the binding
+    against fields added to the header)."""
+    import subprocess
+
+    sys.path.insert(0, os.path.join(ROOT, "ngs-bits_b200"))
+    import seqpurge_b200 as sp
+
+    pairs = {"spg_params": sp._Params, "spg_slot_view": sp._SlotView, "spg_ec_stats": sp._EcStats, "spg_qc_stats": sp._QcStats, "spg_fq_config": sp._FqConfig,
+             "spg_fq_input": sp._FqInput, "spg_fq_output": sp._FqOutput, "spg_synth_config": sp._SynthConfig}
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "seqpurge_b200.h"\nint main(void){' + "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs) + "return 0;}\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    sizes = dict(line.split() for line in out.strip().split("\n"))
+    for name, ct in pairs.items():
+        assert int(sizes[name]) == ctypes.sizeof(ct), name
