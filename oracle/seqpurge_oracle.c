@@ -571,3 +571,40 @@ void spo_qc_update_batch(const uint8_t* bases1, const uint8_t* quals1, const uin
 		qc_update(bases2 + off, quals2 + off, len2[r], 1, out);
 	}
 }
+
+void spo_qc_update_read(const uint8_t* bases, const uint8_t* quals, int len, int reverse, spo_qc_stats* out) { qc_update(bases, quals, len, reverse, out); }
+
+/* FastqEntry::validate (src/cppNGS/FastqFileStream.cpp:3-48), short reads; the checks in the reference's order */
+int spo_validate_entry(const char* header, int header_len, const char* bases, int bases_len, const char* header2, int header2_len, const char* quals, int quals_len)
+{
+	if (header_len == 0 || header[0] != '@') return 1;    /* :7-10 */
+	if (header2_len == 0 || header2[0] != '+') return 2;  /* :11-14 */
+	if (bases_len != quals_len) return 3;                 /* :15-18 */
+	for (int i = 0; i < bases_len; ++i)                   /* :19-25 */
+	{
+		char c = bases[i];
+		if (c != 'A' && c != 'C' && c != 'G' && c != 'T' && c != 'N') return 4;
+	}
+	for (int i = 0; i < quals_len; ++i) /* :26-45 */
+	{
+		int value = quals[i];
+		if (value < 33 || value > 74) return 5;
+	}
+	return 0;
+}
+
+/* src/FastqTrim/main.cpp:47-77 */
+int spo_fastq_trim(int len, int start, int end, int max_bases, int max_len, int* first, int* count)
+{
+	*first = 0;
+	*count = len;
+	if (max_len > 0 && len >= max_len) return 1; /* :52-56: written unchanged */
+	if (start > 0 || end > 0)                     /* :58-64 */
+	{
+		if (len <= start + end) return 0;
+		*first = start;
+		*count = len - start - end;
+	}
+	if (max_bases > 0 && *count > max_bases) *count = max_bases; /* :66-70 */
+	return 1;
+}

@@ -91,6 +91,19 @@ typedef struct spo_qc_stats
 void spo_qc_update_batch(const uint8_t* bases1, const uint8_t* quals1, const uint8_t* bases2, const uint8_t* quals2, const uint16_t* len1, const uint16_t* len2,
                          int stride, int64_t n, spo_qc_stats* out);
 
+/* StatisticsReads::update for ONE read (direction 0 = FORWARD, 1 = REVERSE), as the ReadQC tool calls it per entry of -in1 / -in2
+   (src/ReadQC/main.cpp:64-86) */
+void spo_qc_update_read(const uint8_t* bases, const uint8_t* quals, int len, int reverse, spo_qc_stats* out);
+
+/* FastqEntry::validate for short reads (src/cppNGS/FastqFileStream.cpp:3-48), which ReadQC's reader runs on every entry:
+   0 = valid, 1 = header does not start with '@', 2 = header2 does not start with '+', 3 = |bases| != |qualities|,
+   4 = base outside ACGTN, 5 = quality character outside 33..74 */
+int spo_validate_entry(const char* header, int header_len, const char* bases, int bases_len, const char* header2, int header2_len, const char* quals, int quals_len);
+
+/* The trimming rule of the FastqTrim tool for one read of `len` bases (src/FastqTrim/main.cpp:47-77). Returns 0 if the read is
+   dropped, else 1 with the kept range [*first, *first + *count). */
+int spo_fastq_trim(int len, int start, int end, int max_bases, int max_len, int* first, int* count);
+
 void spo_default_params(spo_params* p);
 
 /* BasicStatistics::factorial / matchProbability (src/cppCORE/BasicStatistics.cpp:249-307).

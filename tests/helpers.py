@@ -55,6 +55,42 @@ def oracle_qc(batch):
     return _qc_to_dict(st)
 
 
+def read_fastq4(path):
+    """All four lines of every record (header, bases, header2, qualities)."""
+    with gzip.open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    return [tuple(l.rstrip(b"\r") for l in (lines[i : i + 4] + [b""] * 4)[:4]) for i in range(0, len(lines), 4)]
+
+
+def oracle_readqc(files1, files2=()):
+    """The ReadQC tool by the oracle (src/ReadQC/main.cpp:58-101): every entry of every file is validated and goes through
+    StatisticsReads::update; returns the accumulators as a dict. Raises ValueError(code) on the first invalid entry."""
+    lib = oracle_lib()
+    st = _SpoQc()
+    for i, f1 in enumerate(files1):
+        for direction, path in ((0, f1),) + (((1, files2[i]),) if i < len(files2) else ()):
+            for h, b, h2, q in read_fastq4(path):
+                code = lib.spo_validate_entry(h, len(h), b, len(b), h2, len(h2), q, len(q))
+                if code:
+                    raise ValueError(code)
+                lib.spo_qc_update_read(b, q, len(b), direction, C.byref(st))
+    return _qc_to_dict(st)
+
+
+def oracle_fastq_trim(records, start=0, end=0, max_bases=0, max_len=0):
+    """The FastqTrim tool by the oracle (src/FastqTrim/main.cpp:47-77) on (header, bases, header2, qualities) records -> FASTQ text."""
+    lib = oracle_lib()
+    out = []
+    first, count = C.c_int(0), C.c_int(0)
+    for h, b, h2, q in records:
+        if lib.spo_fastq_trim(len(b), start, end, max_bases, max_len, C.byref(first), C.byref(count)):
+            s, n = first.value, count.value
+            out.append(h + b"\n" + b[s : s + n] + b"\n" + h2 + b"\n" + q[s : s + n] + b"\n")
+    return b"".join(out)
+
+
 def qc_metrics(d):
     """The eight paired-end quality parameters of StatisticsReads::getResult (src/cppNGS/StatisticsReads.cpp:140-200) as the strings
     a qcML file holds (QCValue::toString: integers as such, doubles with two decimals)."""
@@ -101,6 +137,12 @@ def oracle_lib():
         lib.spo_trim_batch.restype = None
         lib.spo_qc_update_batch.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int64, C.POINTER(_SpoQc)]
         lib.spo_qc_update_batch.restype = None
+        lib.spo_qc_update_read.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.POINTER(_SpoQc)]
+        lib.spo_qc_update_read.restype = None
+        lib.spo_validate_entry.argtypes = [C.c_char_p, C.c_int] * 4
+        lib.spo_validate_entry.restype = C.c_int
+        lib.spo_fastq_trim.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int)] * 2
+        lib.spo_fastq_trim.restype = C.c_int
         lib.spo_match_probability.argtypes = [C.c_double, C.c_int, C.c_int]
         lib.spo_match_probability.restype = C.c_double
         lib.spo_factorial.argtypes = [C.c_int]

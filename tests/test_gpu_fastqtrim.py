@@ -91,7 +91,9 @@ def test_rule_on_random_reads(tool, params, tmp_path):
         cmd = [tool, "-in", str(src), "-out", str(out), "-start", str(start), "-end", str(end), "-len", str(ln), "-max_len", str(max_len)] + extra
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
-        assert content(out) == text_of(fastq_trim_rule(recs, start, end, ln, max_len))
+        want = H.oracle_fastq_trim(recs, start, end, ln, max_len)  # oracle/: C restatement pinned to the reference's goldens (test_oracle_golden.py)
+        assert want == text_of(fastq_trim_rule(recs, start, end, ln, max_len))
+        assert content(out) == want
 
 
 def test_gz_bytes_of_the_serial_writer(tool, tmp_path):

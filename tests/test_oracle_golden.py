@@ -7,6 +7,7 @@
 import ctypes as C
 import gzip
 import os
+import re
 import subprocess
 
 import numpy as np
@@ -147,3 +148,74 @@ def test_qc_statistics_invariants():
     # cycle c is covered by the reads longer than c
     cover = np.array([(b.len1 > c).sum() + (b.len2 > c).sum() for c in range(b.stride)])
     assert np.array_equal(d["pileup"].sum(axis=1)[: b.stride], cover)
+
+
+# ---- the sibling tools on the same infrastructure: ReadQC and FastqTrim ---------------------------------------
+
+
+def _qcml_values(path):
+    vals = []
+    with open(path, encoding="latin-1") as f:
+        for line in f:
+            m = re.search(r'<qualityParameter ID="qp\d+" name="([^"]+)".* value="([^"]*)"', line)
+            if m:
+                vals.append((m.group(1), m.group(2)))
+    return vals
+
+
+READQC_CASES = [
+    ("base_test", [1], [2], "ReadQC_out1.qcML"),
+    ("single_end", [1], [], "ReadQC_out3.qcML"),
+    ("different_read_lengths", [3], [4], "ReadQC_out4.qcML"),  # holds the exact tie 0.125 MB -> "0.13"
+    ("multiple_input_files", [1, 3], [2, 4], "ReadQC_out5.qcML"),
+]
+
+
+@pytest.mark.parametrize("case", READQC_CASES, ids=[c[0] for c in READQC_CASES])
+def test_readqc_oracle_reproduces_reference_goldens(case):
+    """src/tools-TEST/ReadQC_Test.cpp:8-44: the eight quality parameters of the reference's golden qcML files from the oracle's
+    restatement of FastqEntry::validate + StatisticsReads::update / getResult."""
+    _, in1, in2, golden = case
+    d = H.oracle_readqc([f"{G}/ReadQC_in{k}.fastq.gz" for k in in1], [f"{G}/ReadQC_in{k}.fastq.gz" for k in in2])
+    assert d["errors"] == 0
+    want = _qcml_values(f"{G}/{golden}")
+    assert len(want) == 8
+    assert H.qc_metrics(d) == want
+
+
+def test_readqc_oracle_txt_output():
+    d = H.oracle_readqc([f"{G}/ReadQC_in1.fastq.gz"], [f"{G}/ReadQC_in2.fastq.gz"])
+    text = "".join(f"{k}: {v}\n" for k, v in H.qc_metrics(d))
+    assert text == open(f"{G}/ReadQC_out2.txt").read()  # ReadQC_Test.cpp:17-21
+
+
+def test_validate_entry_codes():
+    lib = H.oracle_lib()
+
+    def v(h, b, h2, q):
+        return lib.spo_validate_entry(h, len(h), b, len(b), h2, len(h2), q, len(q))
+
+    assert v(b"@r", b"ACGTN", b"+", b"!IIIJ") == 0
+    assert v(b"r", b"ACGT", b"+", b"IIII") == 1 and v(b"", b"", b"+", b"") == 1
+    assert v(b"@r", b"ACGT", b"-", b"IIII") == 2 and v(b"@r", b"ACGT", b"", b"IIII") == 2
+    assert v(b"@r", b"ACGT", b"+", b"III") == 3
+    assert v(b"@r", b"ACgT", b"+", b"IIII") == 4 and v(b"@r", b"AC-T", b"+", b"IIII") == 4
+    assert v(b"@r", b"ACGT", b"+", b"IIKI") == 5 and v(b"@r", b"ACGT", b"+", b"II I") == 5
+
+
+FASTQTRIM_CASES = [  # src/tools-TEST/FastqTrim_Test.cpp:7-36
+    ("start", 1, dict(start=5)),
+    ("start_end", 2, dict(start=5, end=5)),
+    ("start_len", 3, dict(start=5, max_bases=50)),
+    ("max_len", 4, dict(end=5, max_len=80)),
+    ("all", 5, dict(max_bases=50, start=5, end=5, max_len=80)),
+]
+
+
+@pytest.mark.parametrize("case", FASTQTRIM_CASES, ids=[c[0] for c in FASTQTRIM_CASES])
+def test_fastqtrim_oracle_reproduces_reference_goldens(case):
+    _, k, params = case
+    recs = H.read_fastq4(f"{G}/FastqTrim_in1.fastq.gz")
+    with gzip.open(f"{G}/FastqTrim_out{k}.fastq.gz", "rb") as f:
+        want = f.read()
+    assert H.oracle_fastq_trim(recs, **params) == want
