@@ -75,3 +75,32 @@ def test_ctypes_structs_have_the_sizes_the_compiler_gives_the_header(tmp_path):
     sizes = dict(line.split() for line in out.strip().split("\n"))
     for name, ct in pairs.items():
         assert int(sizes[name]) == ctypes.sizeof(ct), name
+
+
+def test_command_lines_fail_loudly_without_a_gpu(lib, tmp_path):
+    """seqpurge_b200 / readqc_b200 / fastqtrim_b200: usage errors are reported as such, and on a box without a CUDA device the tools stop
+    with the engine's error instead of computing anything on the CPU."""
+    import gzip
+    import subprocess
+
+    import torch
+
+    bin_dir = os.path.join(ROOT, "ngs-bits_b200", "bin")
+    fq = tmp_path / "r.fastq.gz"
+    with gzip.open(fq, "wb") as f:
+        f.write(b"@r1\nACGTACGTAC\n+\nIIIIIIIIII\n")
+    for tool, usage_args, run_args in (
+        ("seqpurge_b200", [], ["-in1", str(fq), "-in2", str(fq), "-out1", str(tmp_path / "a.gz"), "-out2", str(tmp_path / "b.gz")]),
+        ("readqc_b200", [], ["-in1", str(fq), "-txt"]),
+        ("fastqtrim_b200", ["-in", str(fq)], ["-in", str(fq), "-out", str(tmp_path / "c.gz"), "-start", "1"]),
+    ):
+        exe = os.path.join(bin_dir, tool)
+        assert os.path.exists(exe), exe
+        r = subprocess.run([exe] + usage_args, capture_output=True, text=True)
+        assert r.returncode == 1 and "Mandatory parameter" in r.stderr, (tool, r.stderr)
+        r = subprocess.run([exe, "-nonsense"], capture_output=True, text=True)
+        assert r.returncode == 1 and "Unknown parameter" in r.stderr, (tool, r.stderr)
+        assert subprocess.run([exe, "--help"], capture_output=True, text=True).returncode == 0
+        if not torch.cuda.is_available():
+            r = subprocess.run([exe] + run_args, capture_output=True, text=True)
+            assert r.returncode == 1 and "CUDA" in r.stderr, (tool, r.stderr)
