@@ -85,3 +85,21 @@ for name in runs:
     same = all(open(f"{d}/oracle_cli/{f}", "rb").read() == open(f"{d}/{name}/{f}", "rb").read() for f in ("o1.fastq.gz", "o2.fastq.gz"))
     content = all(subprocess.run(f"bash -c 'cmp <(gzip -dc {d}/oracle_cli/{f}) <(gzip -dc {d}/{name}/{f})'", shell=True).returncode == 0 for f in ("o1.fastq.gz", "o2.fastq.gz"))
     print(f"{name}: .gz bytes identical to the oracle: {same}; decompressed content identical: {content}")
+
+# ---- the sibling tools on the same inputs (reads/s; ReadQC and FastqTrim of ngs-bits have no CPU restatement with a command line here)
+if os.environ.get("SPG_CLI_TOOLS", "1") != "0":
+    bin_dir = os.path.join(ROOT, "ngs-bits_b200", "bin")
+    tools = {
+        "readqc_b200 gz in, paired": ([f"{bin_dir}/readqc_b200", "-in1", f"{d}/in1.fastq.gz", "-in2", f"{d}/in2.fastq.gz", "-txt", "-out", f"{d}/qc1.txt"], 2 * n),
+        f"readqc_b200 bgzf in, paired, -threads {threads}": ([f"{bin_dir}/readqc_b200", "-in1", bgz[1], "-in2", bgz[2], "-txt", "-out", f"{d}/qc2.txt", "-threads", str(threads)], 2 * n),
+        "fastqtrim_b200 gz in -> gz out": ([f"{bin_dir}/fastqtrim_b200", "-in", f"{d}/in1.fastq.gz", "-out", f"{d}/ft1.fastq.gz", "-start", "5", "-end", "5"], n),
+        f"fastqtrim_b200 bgzf in -> bgzf out, -threads {threads}": ([f"{bin_dir}/fastqtrim_b200", "-in", bgz[1], "-out", f"{d}/ft2.fastq.gz", "-start", "5", "-end", "5", "-threads", str(threads), "-bgzf"], n),
+    }
+    for name, (cmd, reads) in tools.items():
+        t0 = time.perf_counter()
+        subprocess.run(cmd, check=True)
+        el = time.perf_counter() - t0
+        print(f"{name}: {el:.2f} s for {reads} reads = {reads / el / 1e6:.3f} Mreads/s end to end", flush=True)
+    print("readqc outputs identical:", open(f"{d}/qc1.txt").read() == open(f"{d}/qc2.txt").read(), "| fastqtrim outputs identical:",
+          subprocess.run(f"bash -c 'cmp <(gzip -dc {d}/ft1.fastq.gz) <(gzip -dc {d}/ft2.fastq.gz)'", shell=True).returncode == 0)
+    print(open(f"{d}/qc1.txt").read())
