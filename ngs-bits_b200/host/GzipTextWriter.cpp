@@ -132,21 +132,21 @@ void GzipTextWriter::compressPiece(Piece* p)
 		p->crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), p->text.data(), (uInt)p->text.size());
 		std::lock_guard<std::mutex> g(mu_);
 		p->done = true;
+		cv_.notify_all(); // under the lock: once `done` is visible the writer may be closed and destroyed, this task must not touch it afterwards
 	}
 	catch (...)
 	{
 		std::lock_guard<std::mutex> g(mu_);
 		if (!failure_) failure_ = std::current_exception();
 		p->done = true;
+		cv_.notify_all();
 	}
-	cv_.notify_all();
 }
 
 // the piece as a sequence of BGZF blocks (SAM specification, section 4.1): 18 bytes of header with the block size, raw deflate of at
 // most 0xff00 bytes of text, CRC32, ISIZE
 void GzipTextWriter::compressPieceBgzf(Piece* p)
 {
-	bool failed = false;
 	try
 	{
 		constexpr size_t kBlockText = 0xff00;
@@ -186,16 +186,14 @@ void GzipTextWriter::compressPieceBgzf(Piece* p)
 	}
 	catch (...)
 	{
-		failed = true;
 		std::lock_guard<std::mutex> g(mu_);
 		if (!failure_) failure_ = std::current_exception();
 	}
-	(void)failed;
 	{
 		std::lock_guard<std::mutex> g(mu_);
 		p->done = true;
+		cv_.notify_all(); // under the lock, see compressPiece
 	}
-	cv_.notify_all();
 }
 
 void GzipTextWriter::writerLoop()

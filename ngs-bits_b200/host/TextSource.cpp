@@ -204,8 +204,8 @@ private:
 			std::lock_guard<std::mutex> g(mu_);
 			j->error = error;
 			j->done = true;
+			cv_.notify_all(); // under the lock: once `done` is visible the source may be destroyed, this task must not touch it afterwards
 		}
-		cv_.notify_all();
 	}
 
 	void feed()
