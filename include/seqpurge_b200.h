@@ -245,7 +245,13 @@ void spg_fq_close(spg_fq* fq);
 #define SPG_OPT_TILE_PAIRS 4      /* pairs per TMA-staged tile (multiple of 8; 0 = automatic) */
 #define SPG_OPT_STAGES 5          /* depth of the TMA ring, 2..4 (0 = automatic) */
 #define SPG_OPT_FULL_LEN 6        /* read length the kernel variant is chosen for (fast path for full-length pairs): -1 = automatic, 0 = general kernel only */
+#define SPG_OPT_KERNEL 7          /* thread layout of the read-length variants: 0 = automatic (one lane per pair where it applies), 1 = one warp per pair, 2 = as 0 */
 int spg_set_option(spg_ctx* ctx, int option, int value);
+
+/* Which trimming kernel the last launch of this context ran (bench.py reports it next to the roofline): writes the instantiation's name
+   into name[cap]; returns layout * 100000 + NW * 1000 + FULL (layout 0: general kernel, 1: warp per pair, 2: lane per pair), 0 before
+   the first launch. */
+int spg_last_kernel(spg_ctx* ctx, char* name, int cap);
 
 /* number of kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
 int64_t spg_launch_count(spg_ctx* ctx);

@@ -6,6 +6,7 @@
 // streams, and launches spg::trim_kernel. No CPU implementation of the trimming itself exists in this library.
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +18,7 @@
 #include <algorithm>
 
 #include "spg_kernel.cuh"
+#include "spg_lanes.cuh"
 #include "spg_qc.cuh"
 #include "spg_fastq.cuh"
 
@@ -208,9 +210,18 @@ struct Device
 	double* d_psmall = nullptr;
 	unsigned long long* d_ec = nullptr; // 3 * SPG_MAXLEN
 	unsigned long long* d_qc = nullptr; // spg::kQcWords accumulators of the -qc statistics
-	int occ[4][3] = {};                 // resident CTAs per SM for NW = 0,5,8,10 x kernel variant (min blocks 2,3,4)
-	int full_occ[4][9] = {};            // same for the variants compiled for one read length (full_index)
-	int qc_occ[3] = {};                 // same for qc_kernel, NW = 5,8,10
+	// per kernel instantiation: the dynamic shared memory the function attribute was raised to, and the resident CTAs per SM the
+	// occupancy calculator gave for the last (threads, smem) it was asked about. Guarded by spg_ctx::mu.
+	struct Occ
+	{
+		size_t smem_attr = 0; // cudaFuncAttributeMaxDynamicSharedMemorySize set so far
+		size_t smem = 0;      // launch geometry the cached value belongs to (0: none yet)
+		int ctas = 0;
+	};
+	Occ occ[4][3];      // NW = 0,5,8,10 x kernel variant (min blocks 2,3,4)
+	Occ full_occ[4][9]; // the variants compiled for one read length (full_index)
+	Occ lane_occ[4][9]; // the lane-per-pair kernels of the same read lengths
+	Occ qc_occ[3];      // qc_kernel, NW = 5,8,10
 };
 
 enum SlotState
@@ -259,6 +270,8 @@ struct spg_ctx
 	int tile_pairs = 0; // 0 = automatic
 	int stages = 0;     // 0 = automatic
 	long long launches = 0;
+	int kernel_layout = 0;             // SPG_OPT_KERNEL: 0 automatic, 1 warp per pair only, 2 lane per pair where it applies
+	std::atomic<int> last_kernel{0};   // spg_last_kernel: layout * 100000 + NW * 1000 + FULL of the last trimming launch
 	std::vector<spg_fq*> fqs; // FASTQ streams attached to this context (closed by spg_destroy if the caller did not)
 };
 
@@ -305,34 +318,83 @@ void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 #endif
 constexpr int kCW = SPG_CW; // consumer warps per CTA (+1 producer warp); geometry sweeps showed 4/6/8 within 3%
 
-template <int NW, int MINB, int FULL = 0>
-cudaError_t launch_cfg(const spg::KArgs& a, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, int* occ_cache)
+// Resident CTAs per SM of one kernel instantiation for a launch with `smem` bytes of dynamic shared memory. The function attribute
+// is raised whenever a launch needs more than it was set to (one context launches the same instantiation with different row strides,
+// hence different ring sizes: a later, larger request must not meet the first launch's limit), and the occupancy is asked again
+// whenever the geometry differs from the cached one. `mu` serialises the cache (slots may be submitted from different threads).
+template <typename K>
+cudaError_t resident_ctas(K kernel, Device::Occ& c, int threads, size_t smem, std::mutex& mu, int& out)
 {
-	// per (device, instantiation): raise the dynamic shared memory limit once, ask the occupancy calculator once
-	if (*occ_cache == 0)
+	std::lock_guard<std::mutex> g(mu);
+	if (smem > c.smem_attr)
 	{
-		cudaError_t e = cudaFuncSetAttribute(spg::trim_kernel<NW, kCW, MINB, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 		if (e != cudaSuccess) return e;
-		int n = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::trim_kernel<NW, kCW, MINB, FULL>, (kCW + 1) * 32, smem);
-		if (e != cudaSuccess) return e;
-		*occ_cache = n < 1 ? 1 : n;
+		c.smem_attr = smem;
 	}
-	const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, *occ_cache) : *occ_cache;
+	if (c.ctas == 0 || c.smem != smem)
+	{
+		int n = 0;
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem);
+		if (e != cudaSuccess) return e;
+		c.ctas = n < 1 ? 1 : n;
+		c.smem = smem;
+	}
+	out = c.ctas;
+	return cudaSuccess;
+}
+
+template <int NW, int MINB, int FULL = 0>
+cudaError_t launch_cfg(const spg::KArgs& a, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
+{
+	int occ = 1;
+	cudaError_t e = resident_ctas(spg::trim_kernel<NW, kCW, MINB, FULL>, *occ_cache, (kCW + 1) * 32, smem, mu, occ);
+	if (e != cudaSuccess) return e;
+	const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : occ;
 	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * per_sm);
 	spg::trim_kernel<NW, kCW, MINB, FULL><<<grid, (kCW + 1) * 32, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 
 template <int NW>
-cudaError_t launch_nw(const spg::KArgs& a, int minb, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, int* occ_cache)
+cudaError_t launch_nw(const spg::KArgs& a, int minb, int sm_count, int ctas_per_sm, long long n_tiles, size_t smem, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
 {
 	switch (minb)
 	{
-		case 2: return launch_cfg<NW, 2>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
-		case 4: return launch_cfg<NW, 4>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
-		default: return launch_cfg<NW, 3>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache);
+		case 2: return launch_cfg<NW, 2>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache, mu);
+		case 4: return launch_cfg<NW, 4>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache, mu);
+		default: return launch_cfg<NW, 3>(a, sm_count, ctas_per_sm, n_tiles, smem, stream, occ_cache, mu);
 	}
+}
+
+// The lane-per-pair kernel (spg_lanes.cuh) of one read length: 8 consumer warps + 1 producer warp, compiled for 2 resident CTAs per
+// SM. The ring is as deep as two resident CTAs allow (2..4 stages of 32 pairs' base rows).
+#ifndef SPG_LANE_CW
+#define SPG_LANE_CW 8
+#endif
+#ifndef SPG_LANE_MINB
+#define SPG_LANE_MINB 2
+#endif
+constexpr int kLaneCW = SPG_LANE_CW, kLaneMinB = SPG_LANE_MINB;
+template <int NW, int FULL>
+cudaError_t launch_lanes(spg::KArgs a, int sm_count, int ctas_per_sm, int stages_opt, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
+{
+	const size_t stage = spg::lane_stage_bytes(a.stride);
+	const size_t warps = (size_t)kLaneCW * spg::LaneSmem<NW>::kWarpBytes;
+	int stages = 4;
+	while (stages > 2 && kLaneMinB * (stages * stage + warps + 6 * 1024) > 227 * 1024) --stages;
+	if (stages_opt >= 2 && stages_opt <= spg::kLaneStagesMax) stages = stages_opt;
+	a.stages = stages;
+	a.tile_pairs = 32;
+	const size_t smem = stages * stage + warps;
+	int occ = 1;
+	cudaError_t e = resident_ctas(spg::trim_lanes_kernel<NW, FULL, kLaneCW, kLaneMinB>, *occ_cache, (kLaneCW + 1) * 32, smem, mu, occ);
+	if (e != cudaSuccess) return e;
+	const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : occ;
+	const long long n_tiles = (a.n_pairs + 31) / 32;
+	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * per_sm);
+	spg::trim_lanes_kernel<NW, FULL, kLaneCW, kLaneMinB><<<grid, (kLaneCW + 1) * 32, smem, stream>>>(a);
+	return cudaGetLastError();
 }
 
 // Kernel variants compiled for one read length (fast path for pairs of two full-length reads, spg_kernel.cuh): the usual
@@ -431,14 +493,41 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 
 	const int nw = nw_for_stride(stride);
 	const int cw = ctx->min_blocks;
-	int* occ = &d.occ[nw_index(nw)][cw == 2 ? 0 : cw == 4 ? 2 : 1];
+	Device::Occ* occ = &d.occ[nw_index(nw)][cw == 2 ? 0 : cw == 4 ? 2 : 1];
 	const long long n_tiles = (n + a.tile_pairs - 1) / a.tile_pairs;
 	cudaError_t e;
 	const int fi = (cw == SPG_FULL_MINB && full_hint <= stride && !a.force_bytewise && a.full_ok) ? full_index(nw, full_hint) : 0;
-	if (fi > 0)
+	// the lane-per-pair kernel serves the read-length variants for everything but -ec (rows are edited in place), quality windows
+	// above 8 and presence fragments longer than the packed adapter planes; SPG_OPT_KERNEL 1 keeps the warp-per-pair kernel
+	const bool lanes = fi > 0 && ctx->kernel_layout != 1 && !p.ec && (p.qcut == 0 || p.qwin <= 8) && p.adapter_overlap <= ctx->a_size;
+	ctx->last_kernel.store(fi > 0 ? (lanes ? 2 : 1) * 100000 + nw * 1000 + full_hint : nw * 1000, std::memory_order_relaxed);
+	if (lanes)
 	{
-		int* focc = &d.full_occ[nw_index(nw)][fi];
-#define SPG_FULL(NW_, FL_) e = launch_cfg<NW_, SPG_FULL_MINB, FL_>(a, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, focc)
+		Device::Occ* locc = &d.lane_occ[nw_index(nw)][fi];
+#define SPG_LANES(NW_, FL_) e = launch_lanes<NW_, FL_>(a, d.sm_count, ctx->ctas_per_sm, ctx->stages, stream, locc, ctx->mu)
+		switch (nw * 16 + fi)
+		{
+			case 5 * 16 + 1: SPG_LANES(5, 150); break;
+			case 5 * 16 + 2: SPG_LANES(5, 151); break;
+			case 5 * 16 + 3: SPG_LANES(5, 100); break;
+			case 5 * 16 + 4: SPG_LANES(5, 101); break;
+			case 5 * 16 + 5: SPG_LANES(5, 125); break;
+			case 5 * 16 + 6: SPG_LANES(5, 126); break;
+			case 5 * 16 + 7: SPG_LANES(5, 75); break;
+			case 5 * 16 + 8: SPG_LANES(5, 76); break;
+			case 8 * 16 + 1: SPG_LANES(8, 250); break;
+			case 8 * 16 + 2: SPG_LANES(8, 251); break;
+			case 8 * 16 + 3: SPG_LANES(8, 200); break;
+			case 8 * 16 + 4: SPG_LANES(8, 201); break;
+			case 10 * 16 + 1: SPG_LANES(10, 300); break;
+			default: SPG_LANES(10, 301); break;
+		}
+#undef SPG_LANES
+	}
+	else if (fi > 0)
+	{
+		Device::Occ* focc = &d.full_occ[nw_index(nw)][fi];
+#define SPG_FULL(NW_, FL_) e = launch_cfg<NW_, SPG_FULL_MINB, FL_>(a, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, focc, ctx->mu)
 		switch (nw * 16 + fi)
 		{
 			case 5 * 16 + 1: SPG_FULL(5, 150); break;
@@ -460,10 +549,10 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	}
 	else switch (nw)
 	{
-		case 5: e = launch_nw<5>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
-		case 8: e = launch_nw<8>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
-		case 10: e = launch_nw<10>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
-		default: e = launch_nw<0>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ); break;
+		case 5: e = launch_nw<5>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ, ctx->mu); break;
+		case 8: e = launch_nw<8>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ, ctx->mu); break;
+		case 10: e = launch_nw<10>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ, ctx->mu); break;
+		default: e = launch_nw<0>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ, ctx->mu); break;
 	}
 	if (e != cudaSuccess) return fail(ctx, SPG_ERR_CUDA, std::string("trim_kernel launch: ") + cudaGetErrorString(e));
 	{
@@ -475,23 +564,17 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 
 // the statistics kernel keeps little state in registers, so its occupancy is set by the ring: 3 stages of the trimming kernel's tile
 template <int NW>
-cudaError_t launch_qc_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, int* occ_cache)
+cudaError_t launch_qc_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
 {
 	size_t smem;
 	tile_geometry(a.stride, a.tile_pairs, a.stages, smem);
 	a.stages = 3;
 	smem = (size_t)a.stages * (4 * (size_t)a.tile_pairs * a.stride + 4 * (size_t)a.tile_pairs);
-	if (*occ_cache == 0)
-	{
-		cudaError_t e = cudaFuncSetAttribute(spg::qc_kernel<NW, kCW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return e;
-		int n = 0;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spg::qc_kernel<NW, kCW>, (kCW + 1) * 32, smem);
-		if (e != cudaSuccess) return e;
-		*occ_cache = n < 1 ? 1 : n;
-	}
+	int occ = 1;
+	cudaError_t e0 = resident_ctas(spg::qc_kernel<NW, kCW>, *occ_cache, (kCW + 1) * 32, smem, mu, occ);
+	if (e0 != cudaSuccess) return e0;
 	const long long n_tiles = (a.n_pairs + a.tile_pairs - 1) / a.tile_pairs;
-	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * *occ_cache);
+	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * occ);
 	spg::qc_kernel<NW, kCW><<<grid, (kCW + 1) * 32, smem, stream>>>(a);
 	return cudaGetLastError();
 }
@@ -517,9 +600,9 @@ int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, con
 	cudaError_t e = cudaSuccess;
 	switch (nw_for_stride(stride))
 	{
-		case 5: e = launch_qc_cfg<5>(a, d.sm_count, stream, &d.qc_occ[0]); break;
-		case 8: e = launch_qc_cfg<8>(a, d.sm_count, stream, &d.qc_occ[1]); break;
-		case 10: e = launch_qc_cfg<10>(a, d.sm_count, stream, &d.qc_occ[2]); break;
+		case 5: e = launch_qc_cfg<5>(a, d.sm_count, stream, &d.qc_occ[0], ctx->mu); break;
+		case 8: e = launch_qc_cfg<8>(a, d.sm_count, stream, &d.qc_occ[1], ctx->mu); break;
+		case 10: e = launch_qc_cfg<10>(a, d.sm_count, stream, &d.qc_occ[2], ctx->mu); break;
 		default:
 		{
 			const long long warps_wanted = std::min<long long>((n + 7) / 8, (long long)d.sm_count * 32); // >= 8 pairs per warp, at most 4 CTAs of 8 warps per SM
@@ -842,6 +925,10 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 		case SPG_OPT_FORCE_BYTEWISE: ctx->force_bytewise = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_GRID_CTAS_PER_SM: ctx->ctas_per_sm = value; return SPG_OK;
 		case SPG_OPT_FULL_LEN: ctx->full_len = value < 0 ? -1 : value; return SPG_OK;
+		case SPG_OPT_KERNEL:
+			if (value < 0 || value > 2) return fail(ctx, SPG_ERR_PARAM, "kernel layout must be 0 (automatic), 1 (warp per pair) or 2 (lane per pair)");
+			ctx->kernel_layout = value;
+			return SPG_OK;
 		case SPG_OPT_MIN_BLOCKS:
 			if (value != 2 && value != 3 && value != 4) return fail(ctx, SPG_ERR_PARAM, "min blocks must be 2, 3 or 4");
 			ctx->min_blocks = value;
@@ -851,8 +938,8 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 			ctx->tile_pairs = value;
 			for (Device& d : ctx->devs)
 			{
-				memset(d.occ, 0, sizeof(d.occ));
-				memset(d.full_occ, 0, sizeof(d.full_occ));
+				for (auto& row : d.occ) for (auto& c : row) c.ctas = 0;
+				for (auto& row : d.full_occ) for (auto& c : row) c.ctas = 0;
 			}
 			return SPG_OK;
 		case SPG_OPT_STAGES:
@@ -860,12 +947,26 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 			ctx->stages = value;
 			for (Device& d : ctx->devs)
 			{
-				memset(d.occ, 0, sizeof(d.occ));
-				memset(d.full_occ, 0, sizeof(d.full_occ));
+				for (auto& row : d.occ) for (auto& c : row) c.ctas = 0;
+				for (auto& row : d.full_occ) for (auto& c : row) c.ctas = 0;
 			}
 			return SPG_OK;
 		default: return fail(ctx, SPG_ERR_PARAM, "unknown option");
 	}
+}
+
+int spg_last_kernel(spg_ctx* ctx, char* name, int cap)
+{
+	if (!ctx) return SPG_ERR_PARAM;
+	const int v = ctx->last_kernel.load(std::memory_order_relaxed);
+	const int layout = v / 100000, nw = (v / 1000) % 100, full = v % 1000;
+	if (name && cap > 0)
+	{
+		if (v == 0) snprintf(name, (size_t)cap, "none");
+		else if (layout == 2) snprintf(name, (size_t)cap, "spg::trim_lanes_kernel<NW=%d,FULL=%d,CW=%d,MINB=%d>", nw, full, kLaneCW, kLaneMinB);
+		else snprintf(name, (size_t)cap, "spg::trim_kernel<NW=%d,CW=%d,MINB=%d,FULL=%d>", nw, kCW, ctx->min_blocks, layout == 1 ? full : 0);
+	}
+	return v;
 }
 
 int64_t spg_launch_count(spg_ctx* ctx)

@@ -19,7 +19,8 @@ LIB_PATH = os.environ.get("SPG_LIB") or os.path.join(os.path.dirname(_HERE), "li
 MAXLEN = 1000
 F_INSERT, F_ADAPTER, F_Q1, F_Q2, F_N1, F_N2 = 1, 2, 4, 8, 16, 32
 PAIR_OK, PAIR_BAD_BASE_R2, PAIR_TOO_LONG, PAIR_BAD_BASE_EC = 0, 1, 2, 3
-OPT_FORCE_BYTEWISE, OPT_GRID_CTAS_PER_SM, OPT_MIN_BLOCKS, OPT_TILE_PAIRS, OPT_STAGES, OPT_FULL_LEN = 1, 2, 3, 4, 5, 6
+OPT_FORCE_BYTEWISE, OPT_GRID_CTAS_PER_SM, OPT_MIN_BLOCKS, OPT_TILE_PAIRS, OPT_STAGES, OPT_FULL_LEN, OPT_KERNEL = 1, 2, 3, 4, 5, 6, 7
+KERNEL_AUTO, KERNEL_WARP_PER_PAIR, KERNEL_LANE_PER_PAIR = 0, 1, 2
 
 RESULT_DTYPE = np.dtype([("len1", "<u2"), ("len2", "<u2"), ("best_offset", "<i2"), ("flags", "u1"), ("status", "u1")])
 assert RESULT_DTYPE.itemsize == 8
@@ -108,6 +109,8 @@ _lib.spg_destroy.argtypes = [C.c_void_p]
 _lib.spg_destroy.restype = None
 _lib.spg_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
 _lib.spg_set_option.restype = C.c_int
+_lib.spg_last_kernel.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+_lib.spg_last_kernel.restype = C.c_int
 _lib.spg_launch_count.argtypes = [C.c_void_p]
 _lib.spg_launch_count.restype = C.c_int64
 _lib.spg_synth_device.argtypes = [C.c_int, C.POINTER(_SynthConfig), C.c_int64, C.c_int64] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
@@ -291,6 +294,13 @@ class Engine:
     @property
     def launch_count(self):
         return int(_lib.spg_launch_count(self._h))
+
+    @property
+    def last_kernel(self):
+        """Name of the trimming kernel instantiation the last launch ran (spg_last_kernel)."""
+        buf = C.create_string_buffer(128)
+        _lib.spg_last_kernel(self._h, buf, 128)
+        return buf.value.decode()
 
     def close(self):
         if self._h:

@@ -29,7 +29,7 @@ def sp():
     return seqpurge_b200
 
 
-def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=None, **params):
+def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=None, kernel=None, expect_kernel=None, **params):
     """Run a Batch through spg_submit/spg_wait (pinned slot, H2D, kernel, D2H). Returns records (+ edited batch, ec stats with ec)."""
     p = sp.TrimmingParameters(**params)
     chunk = chunk or batch.n
@@ -38,6 +38,8 @@ def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=No
         eng.set_option(sp.OPT_FORCE_BYTEWISE, 1)
     if full_len is not None:  # kernel variant compiled for this read length (0: the general kernel)
         eng.set_option(sp.OPT_FULL_LEN, full_len)
+    if kernel is not None:  # thread layout of the read-length variants (sp.KERNEL_WARP_PER_PAIR / sp.KERNEL_LANE_PER_PAIR)
+        eng.set_option(sp.OPT_KERNEL, kernel)
     out = np.zeros(batch.n, sp.RESULT_DTYPE)
     edited = batch.copy() if params.get("ec") else None
     starts = list(range(0, batch.n, chunk))
@@ -63,6 +65,8 @@ def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=No
         if edited is not None:
             _copy_back(eng.slot(s0), edited, st0, n0)
     ec = eng.ec_stats() if params.get("ec") else None
+    if expect_kernel is not None:
+        assert expect_kernel in eng.last_kernel, eng.last_kernel
     eng.close()
     return out, edited, ec
 
@@ -401,9 +405,11 @@ def test_full_length_variant(sp, L):
     batch = _full_batch(L, seed=4000 + L)
     assert int(((batch.len1[: batch.n] == L) & (batch.len2[: batch.n] == L)).sum()) > batch.n // 2
     want, _ = H.oracle_trim(batch)
-    got, _, _ = gpu_trim(sp, batch, full_len=L)
+    got, _, _ = gpu_trim(sp, batch, full_len=L, expect_kernel=f"trim_lanes_kernel<NW={5 if L <= 160 else 8 if L <= 256 else 10},FULL={L},")
     assert_same(got, want, batch)
-    general, _, _ = gpu_trim(sp, batch, full_len=0)
+    warp, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_WARP_PER_PAIR, expect_kernel=f"trim_kernel<NW={5 if L <= 160 else 8 if L <= 256 else 10},CW=8,MINB=3,FULL={L}>")
+    assert_same(warp, want, batch)
+    general, _, _ = gpu_trim(sp, batch, full_len=0, expect_kernel="FULL=0>")
     assert_same(general, want, batch)
 
 
@@ -420,6 +426,121 @@ def test_full_length_variant_parameters(sp, params):
         want, _ = H.oracle_trim(batch, **params)
         got, _, _ = gpu_trim(sp, batch, full_len=L, **params)
         assert_same(got, want, batch)
+        warp, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_WARP_PER_PAIR, **params)
+        assert_same(warp, want, batch)
+
+
+LANE_CASES = {
+    # (read length, row stride, batch keywords, trimming parameters)
+    "plain_150_tight": (150, 150, dict(insert_mean=160, insert_sd=90, error_rate=0.01, n_rate=0.0, lowq_tail=4.0), dict()),
+    "plain_150_wide_rows": (150, 160, dict(insert_mean=160, insert_sd=90, error_rate=0.03, n_rate=0.0, lowq_tail=4.0), dict()),
+    "long_lowq_tails": (150, 150, dict(insert_mean=200, insert_sd=90, error_rate=0.02, n_rate=0.0, lowq_tail=40.0), dict(qcut=20)),
+    "windows_1_to_8": (126, 126, dict(insert_mean=100, insert_sd=60, error_rate=0.02, n_rate=0.0, lowq_tail=12.0), dict(qwin=8, qcut=25)),
+    "window_1": (101, 102, dict(insert_mean=100, insert_sd=60, error_rate=0.02, n_rate=0.0, lowq_tail=12.0), dict(qwin=1, qcut=30)),
+    "no_quality_trimming": (75, 76, dict(insert_mean=60, insert_sd=40, error_rate=0.02, n_rate=0.0005), dict(qcut=0, ncut=0)),
+    "all_overlap_250": (250, 250, dict(insert_mean=150, insert_sd=60, error_rate=0.02, n_rate=0.0), dict()),
+    "short_inserts_300": (300, 300, dict(insert_mean=40, insert_sd=60, error_rate=0.01, n_rate=0.0001), dict()),
+    "loose_filter": (150, 150, dict(insert_mean=160, insert_sd=90, error_rate=0.08, n_rate=0.0), dict(match_perc=60.0, mep=1e-3)),
+    "n_and_ragged_mix": (151, 152, dict(insert_mean=160, insert_sd=90, error_rate=0.02, n_rate=0.002, n_runs=0.05, lowq_tail=10.0), dict()),
+}
+
+
+@pytest.mark.parametrize("name", list(LANE_CASES), ids=list(LANE_CASES))
+def test_lane_per_pair_kernel(sp, name):
+    """The lane-per-pair layout of the read-length variants (spg_lanes.cuh) against the oracle and against the warp-per-pair kernel:
+    tight and wide row strides (rows that start in the middle of a word), pair counts that leave the last 32-pair tile ragged,
+    trimming points far from the 3' end (several blocks of the per-lane quality search), all window sizes the layout serves."""
+    L, stride, kw, params = LANE_CASES[name]
+    n = 32 * 37 + 13
+    batch = H.random_batch(n, L, seed=5000 + L + len(name), stride=stride, **kw)
+    if name == "n_and_ragged_mix":
+        r = H.random_batch(200, L, seed=9, ragged=True, stride=stride)
+        for j in range(200):
+            for k in ("bases1", "quals1", "bases2", "quals2", "len1", "len2"):
+                getattr(batch, k)[5 * j + 1] = getattr(r, k)[j]
+    want, _ = H.oracle_trim(batch, **params)
+    got, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_LANE_PER_PAIR, expect_kernel="trim_lanes_kernel", **params)
+    assert_same(got, want, batch)
+    warp, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_WARP_PER_PAIR, expect_kernel="trim_kernel", **params)
+    assert_same(warp, want, batch)
+
+
+def test_lane_per_pair_low_complexity_reads(sp):
+    """Homopolymer and short-period reads: every insert offset survives the pre-filter, far more than a lane can queue -- such pairs
+    must take the general path and still agree with the oracle."""
+    L = 150
+    batch = H.random_batch(32 * 6, L, seed=12, stride=L, n_rate=0.0)
+    for i in range(0, batch.n, 3):
+        batch.bases1[i, :L] = ord("A")
+        batch.bases2[i, :L] = ord("T")
+    for i in range(1, batch.n, 3):
+        batch.bases1[i, :L] = np.frombuffer((b"AC" * L)[:L], np.uint8)
+        batch.bases2[i, :L] = np.frombuffer((b"GT" * L)[:L], np.uint8)
+    want, _ = H.oracle_trim(batch)
+    got, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_LANE_PER_PAIR, expect_kernel="trim_lanes_kernel")
+    assert_same(got, want, batch)
+
+
+@pytest.mark.parametrize("stages,ctas", [(2, 1), (3, 2), (4, 0)])
+def test_lane_per_pair_ring_many_rounds(sp, stages, ctas):
+    """Many tiles per CTA (the ring wraps dozens of times, warps claim tiles further ahead than the ring is deep): the lane-per-pair
+    kernel against the warp-per-pair kernel on every record and against the oracle on a slice."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    n, L = 400_000, 150
+    cfg = sp.SynthConfig(read_len=L, insert_mean=200, insert_sd=80, error_rate=0.005, lowq_tail_mean=6.0)
+    t = {k: torch.empty((n, L), dtype=torch.uint8, device=dev) for k in ("bases1", "quals1", "bases2", "quals2")}
+    l1 = torch.empty(n, dtype=torch.int16, device=dev)
+    l2 = torch.empty(n, dtype=torch.int16, device=dev)
+    sp.synth_device(cfg, 7_000_000, n, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
+    eng = sp.Engine(sp.TrimmingParameters(), devices=(0,))
+    eng.set_option(sp.OPT_FULL_LEN, L)
+    res = {}
+    for layout in (sp.KERNEL_WARP_PER_PAIR, sp.KERNEL_LANE_PER_PAIR):
+        eng.set_option(sp.OPT_KERNEL, layout)
+        if layout == sp.KERNEL_LANE_PER_PAIR:
+            eng.set_option(sp.OPT_STAGES, stages)
+            eng.set_option(sp.OPT_GRID_CTAS_PER_SM, ctas)
+        r = torch.empty((n, 8), dtype=torch.uint8, device=dev)
+        for _ in range(2):
+            eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, r)
+        torch.cuda.synchronize()
+        res[layout] = r
+    assert "trim_lanes_kernel" in eng.last_kernel
+    assert torch.equal(res[sp.KERNEL_WARP_PER_PAIR], res[sp.KERNEL_LANE_PER_PAIR])
+    m = 40_000
+    batch = H.Batch(m, L)
+    for k in t:
+        getattr(batch, k)[:m] = t[k][n - m :].cpu().numpy()
+    batch.len1[:m] = l1[n - m :].cpu().numpy().view(np.uint16)
+    batch.len2[:m] = l2[n - m :].cpu().numpy().view(np.uint16)
+    want, _ = H.oracle_trim(batch, threads=8)
+    assert_same(sp.results_from_tensor(res[sp.KERNEL_LANE_PER_PAIR][n - m :]).copy(), want, batch)
+    eng.close()
+
+
+def test_engine_reuses_kernels_across_row_strides(sp):
+    """One context, device-resident launches of the same kernel instantiation with growing row strides (a stream reopened for longer
+    reads): the shared-memory attribute and the cached occupancy must follow the launch geometry."""
+    import torch
+
+    dev = torch.device("cuda:0")
+    eng = sp.Engine(sp.TrimmingParameters(), devices=(0,))
+    for layout in (sp.KERNEL_WARP_PER_PAIR, sp.KERNEL_LANE_PER_PAIR):
+        eng.set_option(sp.OPT_KERNEL, layout)
+        for L, stride in ((180, 192), (220, 224), (250, 256), (150, 150), (150, 160)):
+            batch = H.random_batch(500, L, seed=L + stride, stride=stride)
+            want, _ = H.oracle_trim(batch)
+            t = {k: torch.from_numpy(getattr(batch, k)).to(dev) for k in ("bases1", "quals1", "bases2", "quals2")}
+            l1 = torch.from_numpy(batch.len1.view(np.int16)).to(dev)
+            l2 = torch.from_numpy(batch.len2.view(np.int16)).to(dev)
+            res = torch.empty((batch.n, 8), dtype=torch.uint8, device=dev)
+            eng.set_option(sp.OPT_FULL_LEN, L)
+            eng.trim_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, res, n_pairs=batch.n)
+            torch.cuda.synchronize()
+            assert_same(sp.results_from_tensor(res).copy(), want, batch)
+    eng.close()
 
 
 def test_full_length_variant_error_correction(sp):
