@@ -270,6 +270,7 @@ struct spg_ctx
 	int tile_pairs = 0; // 0 = automatic
 	int stages = 0;     // 0 = automatic
 	long long launches = 0;
+	int seed_scan = 1;                 // SPG_OPT_SEED_SCAN: 0 = the lane kernel evaluates every offset of the adapter scans (no pigeonhole filter)
 	int kernel_layout = 0;             // SPG_OPT_KERNEL: 0 automatic, 1 warp per pair only, 2 lane per pair where it applies
 	std::atomic<int> last_kernel{0};   // spg_last_kernel: layout * 100000 + NW * 1000 + FULL of the last trimming launch
 	std::vector<spg_fq*> fqs; // FASTQ streams attached to this context (closed by spg_destroy if the caller did not)
@@ -370,7 +371,7 @@ cudaError_t launch_nw(const spg::KArgs& a, int minb, int sm_count, int ctas_per_
 // The lane-per-pair kernel (spg_lanes.cuh) of one read length: 8 consumer warps + 1 producer warp, compiled for 2 resident CTAs per
 // SM. The ring is as deep as two resident CTAs allow (2..4 stages of 32 pairs' base rows).
 #ifndef SPG_LANE_CW
-#define SPG_LANE_CW 8
+#define SPG_LANE_CW 12
 #endif
 #ifndef SPG_LANE_MINB
 #define SPG_LANE_MINB 2
@@ -485,6 +486,24 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 		a.full_ok = ok ? 1 : 0;
 		a.a1maxmm = a.a1pass ? 31 - __builtin_clz(a.a1pass) : -1;
 		a.a2maxmm = a.a2pass ? 31 - __builtin_clz(a.a2pass) : -1;
+		// seed filter of the lane kernel's adapter scans (pigeonhole): a window of tot compared bases that passes must have fewer
+		// mismatches than it holds complete 4-base blocks of the adapter's first 4 * (a_size / 4) bases
+		bool seed = ok && ctx->adapters_plain;
+		for (int tot = 1; tot <= ctx->a_size && seed; ++tot)
+		{
+			int kmax = -1;
+			for (int mm = 0; mm <= tot; ++mm)
+				if ((ctx->tables.passA[tot] >> (tot - mm)) & 1u) kmax = mm;
+			if (kmax >= std::min(tot / 4, ctx->a_size / 4)) seed = false;
+		}
+		a.seed_ok = (seed && ctx->seed_scan) ? 1 : 0;
+		const int nwi = nw_for_stride(stride);
+		auto code = [](char c) { return c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0; };
+		for (int i = 0; i < 20; ++i)
+		{
+			a.a1off[i] = (uint16_t)(i < ctx->a_size ? code(ctx->a1[(size_t)i]) * (nwi + 1) * 128 : 0);
+			a.a2off[i] = (uint16_t)(i < ctx->a_size ? code(ctx->a2[(size_t)i]) * (nwi + 1) * 128 : 0);
+		}
 	}
 	memset(a.a1, 'N', sizeof(a.a1)); // never read beyond the adapter length: a_size, adapter_overlap <= min(|a1|,|a2|,32)
 	memset(a.a2, 'N', sizeof(a.a2));
@@ -925,6 +944,7 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 		case SPG_OPT_FORCE_BYTEWISE: ctx->force_bytewise = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_GRID_CTAS_PER_SM: ctx->ctas_per_sm = value; return SPG_OK;
 		case SPG_OPT_FULL_LEN: ctx->full_len = value < 0 ? -1 : value; return SPG_OK;
+		case SPG_OPT_SEED_SCAN: ctx->seed_scan = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_KERNEL:
 			if (value < 0 || value > 2) return fail(ctx, SPG_ERR_PARAM, "kernel layout must be 0 (automatic), 1 (warp per pair) or 2 (lane per pair)");
 			ctx->kernel_layout = value;

@@ -75,6 +75,9 @@ struct KArgs
 	uint32_t a1pass, a2pass; // bit j: a full-window comparison (all of amask) with j mismatches passes
 	int a1maxmm, a2maxmm;    // the same as a limit: most mismatches with which a full window passes (-1: never); only valid if full_ok
 	int full_ok;             // adapters without N in their first a_size bases and every pass set of steps 2/3 an interval 0..k of mismatches
+	int seed_ok;             // lane kernel: every passing window of steps 2/3 has fewer mismatches than complete 4-base adapter blocks (and full_ok)
+	uint16_t a1off[20];      // lane kernel: byte offset of the base-indicator plane (A,C,G,T -> 0..3 times (NW+1)*128) of adapter position i
+	uint16_t a2off[20];
 	uint32_t passA[21]; // [T] bit m: adapter-only hit with m matches out of T compared bases passes (steps 2/3)
 	uint8_t a1[32];     // adapter bytes (first 32)
 	uint8_t a2[32];

@@ -300,6 +300,77 @@ __device__ __forceinline__ int lane_adapter_scan(const KArgs& A, const FullTab<N
 	return (int)best; // 0xFFFFFFFF -> -1
 }
 
+// The same scan with a bit-parallel filter in front (used when KArgs::seed_ok): a window that passes has fewer mismatches than it
+// holds complete 4-base blocks of the adapter (checked on the host for every window length), so one of those blocks matches the
+// read exactly (pigeonhole). "Block j of the adapter occurs at offset o" is evaluated for 32 offsets per instruction: the read's four
+// base indicators (bit p = base p is A / C / G / T) are kept in shared memory (`ind`, [4][NW+1] words per lane, which of them an
+// adapter position needs comes from KArgs::a?off), shifted by the position inside the adapter and ANDed. Only the offsets that
+// survive (about 2 % of them) get the exact count of lane_adapter_scan, with the same multipliers and limits.
+template <int NW, int FULL>
+__device__ __forceinline__ int lane_adapter_scan_seeds(const KArgs& A, const FullTab<NW, FULL>& F, const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], uint32_t ind,
+                                                       const uint16_t* aoff, uint32_t ah, uint32_t al, int maxmm)
+{
+	constexpr int QF = FullTab<NW, FULL>::QF;
+#pragma unroll
+	for (int w = 0; w < NW; ++w)
+	{
+		sts_u32(ind + (0u * (NW + 1) + w) * 128u, ~(fh[w] | fl[w]) & low_mask_const(FULL - 32 * w)); // A = 00 (also what lies behind the read)
+		sts_u32(ind + (1u * (NW + 1) + w) * 128u, ~fh[w] & fl[w]);                                     // C = 01
+		sts_u32(ind + (2u * (NW + 1) + w) * 128u, fh[w] & fl[w]);                                      // G = 11
+		sts_u32(ind + (3u * (NW + 1) + w) * 128u, fh[w] & ~fl[w]);                                     // T = 10
+	}
+#pragma unroll
+	for (int k = 0; k < 4; ++k) sts_u32(ind + ((uint32_t)k * (NW + 1) + NW) * 128u, 0u);
+	uint32_t cand[NW];
+#pragma unroll
+	for (int w = 0; w < NW; ++w) cand[w] = 0;
+	const int nblk = A.a_size >> 2;
+#pragma unroll 1
+	for (int j = 0; j < nblk; ++j)
+	{
+		uint32_t acc[NW];
+#pragma unroll
+		for (int w = 0; w < NW; ++w) acc[w] = kFull;
+#pragma unroll
+		for (int t = 0; t < 4; ++t)
+		{
+			const int i = 4 * j + t;
+			const uint32_t base = ind + (uint32_t)aoff[i];
+			uint32_t iw[NW + 1];
+#pragma unroll
+			for (int w = 0; w <= NW; ++w) iw[w] = lds_u32(base + 128u * (uint32_t)w);
+#pragma unroll
+			for (int w = 0; w < NW; ++w) acc[w] &= __funnelshift_r(iw[w], iw[w + 1], i); // bit o: read base o+i equals adapter base i
+		}
+#pragma unroll
+		for (int w = 0; w < NW; ++w) cand[w] |= acc[w];
+	}
+	const uint32_t amul = 1u << (32 - A.a_size);
+	uint32_t best = 0xFFFFFFFFu;
+	static_for<NW>([&](auto wc) {
+		constexpr int w = decltype(wc)::value;
+		uint32_t c = cand[w];
+		while (c != 0 && best == 0xFFFFFFFFu)
+		{
+			const int b = __ffs((int)c) - 1;
+			c &= c - 1;
+			const uint32_t sh = __funnelshift_r(fh[w], (w + 1 < NW) ? fh[w + 1 < NW ? w + 1 : 0] : 0u, b);
+			const uint32_t sl = __funnelshift_r(fl[w], (w + 1 < NW) ? fl[w + 1 < NW ? w + 1 : 0] : 0u, b);
+			const uint32_t x = (sh ^ ah) | (sl ^ al);
+			uint32_t mul = amul;
+			int lim = maxmm;
+			if constexpr (w >= QF)
+			{
+				const int2 t = F.r1tail[w - QF][b];
+				mul = (uint32_t)t.x;
+				lim = t.y;
+			}
+			if (__popc(x * mul) <= lim) best = (uint32_t)(32 * w + b);
+		}
+	});
+	return (int)best;
+}
+
 // ---- FastqEntry::trimQuality (src/cppNGS/FastqFileStream.cpp:52-87), one read per lane ----------------------------------------------------
 // Window 5 (the default), trimming point within the last 16 bases: the 16 quality bytes are taken from global memory into
 // registers (only the sectors that hold the end of the read are fetched), the twelve window sums slide down from the 3' end
@@ -419,12 +490,29 @@ __device__ __noinline__ void lane_general_pair(const KArgs& A, const SmemTables&
 	const uint32_t rb = ((uint32_t)A.stride + 3u) & ~3u; // rows of the buffer start on word boundaries
 	const size_t goff = (size_t)p * A.stride;
 	const int halves = A.stride / 2;
-	for (int v = lane; v < halves; v += 32)
+	for (int v0 = 0; v0 < halves; v0 += 128) // up to 16 loads of a lane in flight before the first store
 	{
-		sts_u16(buf + 0 * rb + 2u * v, reinterpret_cast<const uint16_t*>(A.b1 + goff)[v]);
-		sts_u16(buf + 1 * rb + 2u * v, reinterpret_cast<const uint16_t*>(A.q1 + goff)[v]);
-		sts_u16(buf + 2 * rb + 2u * v, reinterpret_cast<const uint16_t*>(A.b2 + goff)[v]);
-		sts_u16(buf + 3 * rb + 2u * v, reinterpret_cast<const uint16_t*>(A.q2 + goff)[v]);
+		uint32_t x[4][4];
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			const int v = v0 + 32 * u + lane;
+			const bool in = v < halves;
+			x[u][0] = in ? reinterpret_cast<const uint16_t*>(A.b1 + goff)[v] : 0u;
+			x[u][1] = in ? reinterpret_cast<const uint16_t*>(A.q1 + goff)[v] : 0u;
+			x[u][2] = in ? reinterpret_cast<const uint16_t*>(A.b2 + goff)[v] : 0u;
+			x[u][3] = in ? reinterpret_cast<const uint16_t*>(A.q2 + goff)[v] : 0u;
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u)
+		{
+			const int v = v0 + 32 * u + lane;
+			if (v < halves)
+			{
+#pragma unroll
+				for (int k = 0; k < 4; ++k) sts_u16(buf + (uint32_t)k * rb + 2u * (uint32_t)v, x[u][k]);
+			}
+		}
 	}
 	__syncwarp();
 	Pair P;
@@ -651,8 +739,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 		int fwd = -1, rev = -1;
 		if (__any_sync(kFull, plain && key == kNoKey))
 		{
-			fwd = lane_adapter_scan<NW, FULL>(A, F, f1h, f1l, A.a1h, A.a1l, A.a1maxmm);
-			rev = lane_adapter_scan<NW, FULL>(A, F, f2h, f2l, A.a2h, A.a2l, A.a2maxmm);
+			if (A.seed_ok)
+			{
+				fwd = lane_adapter_scan_seeds<NW, FULL>(A, F, f1h, f1l, copy, A.a1off, A.a1h, A.a1l, A.a1maxmm);
+				rev = lane_adapter_scan_seeds<NW, FULL>(A, F, f2h, f2l, copy, A.a2off, A.a2h, A.a2l, A.a2maxmm);
+			}
+			else
+			{
+				fwd = lane_adapter_scan<NW, FULL>(A, F, f1h, f1l, A.a1h, A.a1l, A.a1maxmm);
+				rev = lane_adapter_scan<NW, FULL>(A, F, f2h, f2l, A.a2h, A.a2l, A.a2maxmm);
+			}
 		}
 
 		// ---- lengths, quality trimming, record ----

@@ -29,7 +29,7 @@ def sp():
     return seqpurge_b200
 
 
-def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=None, kernel=None, expect_kernel=None, **params):
+def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=None, kernel=None, expect_kernel=None, seed_scan=None, **params):
     """Run a Batch through spg_submit/spg_wait (pinned slot, H2D, kernel, D2H). Returns records (+ edited batch, ec stats with ec)."""
     p = sp.TrimmingParameters(**params)
     chunk = chunk or batch.n
@@ -40,6 +40,8 @@ def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=No
         eng.set_option(sp.OPT_FULL_LEN, full_len)
     if kernel is not None:  # thread layout of the read-length variants (sp.KERNEL_WARP_PER_PAIR / sp.KERNEL_LANE_PER_PAIR)
         eng.set_option(sp.OPT_KERNEL, kernel)
+    if seed_scan is not None:  # lane-per-pair kernel: exact-block filter in front of the adapter scans on / off
+        eng.set_option(sp.OPT_SEED_SCAN, seed_scan)
     out = np.zeros(batch.n, sp.RESULT_DTYPE)
     edited = batch.copy() if params.get("ec") else None
     starts = list(range(0, batch.n, chunk))
@@ -441,6 +443,9 @@ LANE_CASES = {
     "all_overlap_250": (250, 250, dict(insert_mean=150, insert_sd=60, error_rate=0.02, n_rate=0.0), dict()),
     "short_inserts_300": (300, 300, dict(insert_mean=40, insert_sd=60, error_rate=0.01, n_rate=0.0001), dict()),
     "loose_filter": (150, 150, dict(insert_mean=160, insert_sd=90, error_rate=0.08, n_rate=0.0), dict(match_perc=60.0, mep=1e-3)),
+    "adapter_only_hits": (150, 150, dict(insert_mean=140, insert_sd=25, error_rate=0.12, n_rate=0.0, lowq_tail=2.0), dict()),
+    "short_adapters_19": (100, 100, dict(insert_mean=90, insert_sd=25, error_rate=0.1, n_rate=0.0, a1="CTGTCTCTTATACACATCT", a2="CTGTCTCTTATACACATCT"),
+                          dict(a1="CTGTCTCTTATACACATCT", a2="CTGTCTCTTATACACATCT")),
     "n_and_ragged_mix": (151, 152, dict(insert_mean=160, insert_sd=90, error_rate=0.02, n_rate=0.002, n_runs=0.05, lowq_tail=10.0), dict()),
 }
 
@@ -461,6 +466,8 @@ def test_lane_per_pair_kernel(sp, name):
     want, _ = H.oracle_trim(batch, **params)
     got, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_LANE_PER_PAIR, expect_kernel="trim_lanes_kernel", **params)
     assert_same(got, want, batch)
+    every, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_LANE_PER_PAIR, seed_scan=0, **params)  # adapter scans without the filter
+    assert_same(every, want, batch)
     warp, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_WARP_PER_PAIR, expect_kernel="trim_kernel", **params)
     assert_same(warp, want, batch)
 
