@@ -1147,7 +1147,17 @@ __device__ __noinline__ RareSteps steps_special(const KArgs& A, const SmemTables
 	bool hasN1, hasN2, other1, other2;
 	pack_special<NW>(P.r1, P.len1, 0, lane, n1, hasN1, other1);
 	pack_special<NW>(P.r2, P.len2, D2, lane, n2r, hasN2, other2);
-	r.hasN = (hasN1 ? 1 : 0) | (hasN2 ? 2 : 0);
+	{
+		// hasN only gates trimN: a read with fewer than ncut N cannot hold a run of ncut of them
+		int c1 = 0, c2 = 0;
+#pragma unroll
+		for (int w = 0; w < NW; ++w)
+		{
+			c1 += __popc(n1[w]);
+			c2 += __popc(n2r[w]);
+		}
+		r.hasN = (hasN1 && c1 >= A.ncut ? 1 : 0) | (hasN2 && c2 >= A.ncut ? 2 : 0);
+	}
 	if (other2) r.status = SPG_PAIR_BAD_BASE_R2; // Sequence::complement throws (Sequence.cpp:46-71)
 	else if (other1) r.st = steps_bytewise(A, T, P, lane); // read 1 bytes are compared as plain bytes by the reference
 	else

@@ -53,6 +53,12 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c)
 	return d;
 }
 __host__ __device__ constexpr uint32_t low_mask_const(int n) { return n >= 32 ? 0xffffffffu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+__host__ __device__ constexpr uint64_t low_mask64_const(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull)); }
+// Words of an overlap of at most T bases that the pre-filter of the insert sweep looks at: the lo-plane differences inside the
+// first c words are a lower bound of the mismatch count just like those of the whole overlap, and for unrelated reads (half of
+// the lo bits differ) 32c positions exceed a limit of T/5 mismatches by 3.7 standard deviations when 16c - 3.7 sqrt(8c) >= T/5.
+// A weaker filter only means more offsets for the exact count (with a much laxer -match_perc), never a different result.
+__host__ __device__ constexpr int sweep_words(int T) { return T <= 27 ? 1 : T <= 86 ? 2 : T <= 149 ? 3 : T <= 215 ? 4 : T <= 283 ? 5 : 6; }
 
 // ---- per-warp shared memory of the lane path -----------------------------------------------------------------------------------------
 // plane copies [4][NW+1][32 lanes] (read 1 forward hi/lo, read 2 reversed hi/lo; word NW is a zero pad), the quality window
@@ -376,8 +382,9 @@ __device__ __forceinline__ int lane_adapter_scan_seeds(const KArgs& A, const Ful
 // registers (only the sectors that hold the end of the read are fetched), the twelve window sums slide down from the 3' end
 // (sign bits of sum - threshold collected by funnel shifts), "quality >= cutoff" of the 16 bases by one SWAR addition per word.
 // Works on the raw bytes (thresholds shifted by the quality offset), which is the reference's signed-char arithmetic as long as
-// all bytes are below 0x80. Returns the new length, or -1 if this read needs the general search (shorter than 16 bases, a byte
-// >= 0x80, no passing window among the last twelve).
+// all bytes are below 0x80. n: end of the 16 bases looked at (the read's length, or 12, 24, ... less: the search goes on to the left
+// when none of the twelve windows passes). Returns the new length, or -1: no passing window here (or fewer than 16 bases, a byte
+// >= 0x80 -- then the general search decides).
 __device__ __forceinline__ int lane_trim_quality5(const KArgs& A, const uint8_t* qrow, int n)
 {
 	const int cutb = A.qcut + A.qoff, thrb = A.qthr + 5 * A.qoff;
@@ -694,14 +701,20 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 				const uint32_t ta = thr_addr + 2u * (uint32_t)r;
 				static_for<NW>([&](auto qc) {
 					constexpr int q = decltype(qc)::value;
+					constexpr int KMAX = (NW - q) < sweep_words(FULL - 32 * q) ? (NW - q) : sweep_words(FULL - 32 * q);
 					int mml = 0;
 #pragma unroll
-					for (int k = 0; k < NW - q; ++k)
+					for (int k = 0; k < KMAX; ++k)
 					{
 						const int w = q + k;
 						uint32_t x;
 						if (32 * w + 62 < FULL) x = sv[w] ^ f1l[k];
-						else x = xor_and(sv[w], f1l[k], low_bits(FULL - 32 * w - r)); // compared positions: i < FULL - o
+						else
+						{
+							// compared positions: i < FULL - o, i.e. the low FULL - 32w - r bits of this word: a 64-bit constant shifted by r
+							const uint64_t M = low_mask64_const(FULL - 32 * w); // folded after unrolling
+							x = xor_and(sv[w], f1l[k], __funnelshift_r((uint32_t)M, (uint32_t)(M >> 32), r));
+						}
 						mml += __popc(x);
 					}
 					mmlq[q] = mml;
@@ -772,10 +785,17 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 		{
 			const size_t goff = (size_t)p * A.stride;
 			int t1 = -1, t2 = -1;
-			if (A.qwin == 5 && plain) // both reads' last 16 qualities in registers
+			if (A.qwin == 5 && plain) // 16 qualities in registers, twelve window starts at a time from the 3' end
 			{
-				t1 = lane_trim_quality5(A, A.q1 + goff, n1);
-				t2 = lane_trim_quality5(A, A.q2 + goff, n2);
+				int e1 = n1, e2 = n2;
+				for (int k = 0; k < 8; ++k)
+				{
+					if (t1 < 0 && e1 >= 16) t1 = lane_trim_quality5(A, A.q1 + goff, e1);
+					if (t2 < 0 && e2 >= 16) t2 = lane_trim_quality5(A, A.q2 + goff, e2);
+					e1 -= 12;
+					e2 -= 12;
+					if (!((t1 < 0 && e1 >= 16) || (t2 < 0 && e2 >= 16))) break;
+				}
 			}
 			if (__any_sync(kFull, plain && t1 < 0)) t1 = lane_trim_quality(A, A.q1 + goff, n1, plain && t1 < 0, scr, t1);
 			if (__any_sync(kFull, plain && t2 < 0)) t2 = lane_trim_quality(A, A.q2 + goff, n2, plain && t2 < 0, scr, t2);
