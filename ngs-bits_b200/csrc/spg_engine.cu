@@ -9,6 +9,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -382,7 +383,7 @@ cudaError_t launch_lanes(spg::KArgs a, int sm_count, int ctas_per_sm, int stages
 {
 	const size_t stage = spg::lane_stage_bytes(a.stride);
 	const size_t warps = (size_t)kLaneCW * spg::LaneSmem<NW>::kWarpBytes;
-	int stages = 4;
+	int stages = spg::kLaneStagesMax;
 	while (stages > 2 && kLaneMinB * (stages * stage + warps + 6 * 1024) > 227 * 1024) --stages;
 	if (stages_opt >= 2 && stages_opt <= spg::kLaneStagesMax) stages = stages_opt;
 	a.stages = stages;
@@ -436,7 +437,7 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	size_t smem;
 	tile_geometry(stride, a.tile_pairs, a.stages, smem);
 	if (ctx->tile_pairs > 0) a.tile_pairs = ctx->tile_pairs;
-	if (ctx->stages > 0) a.stages = ctx->stages;
+	if (ctx->stages > 0) a.stages = std::min(ctx->stages, spg::kMaxStages);
 	smem = (size_t)a.stages * (4 * (size_t)a.tile_pairs * stride + 4 * (size_t)a.tile_pairs);
 	if (smem > 200 * 1024) return fail(ctx, SPG_ERR_PARAM, "tile geometry exceeds shared memory");
 	a.mmin = d.d_mmin;
@@ -677,6 +678,7 @@ int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, i
 		delete ctx;
 		return fail(nullptr, SPG_ERR_PARAM, err);
 	}
+	if (const char* e = getenv("SPG_STAGES")) ctx->stages = std::max(0, std::min(atoi(e), (int)spg::kLaneStagesMax)); // tuning runs only
 	ctx->max_pairs = max_pairs;
 	ctx->max_len = max_len;
 	ctx->stride = n_slots > 0 ? std::max(16, (max_len + 1) / 2 * 2) : 0; // even: a tile of 8 rows is then a multiple of 16 bytes (TMA)
@@ -963,7 +965,7 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 			}
 			return SPG_OK;
 		case SPG_OPT_STAGES:
-			if (value < 0 || value > spg::kMaxStages || value == 1) return fail(ctx, SPG_ERR_PARAM, "stages must be 2..4");
+			if (value < 0 || value > spg::kLaneStagesMax || value == 1) return fail(ctx, SPG_ERR_PARAM, "stages must be 2..8 (2..4 for the warp-per-pair kernels)");
 			ctx->stages = value;
 			for (Device& d : ctx->devs)
 			{

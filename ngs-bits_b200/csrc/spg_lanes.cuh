@@ -68,7 +68,7 @@ template <int NW>
 struct LaneSmem
 {
 	static constexpr uint32_t kCopyBytes = 4u * (NW + 1) * 128u;
-	static constexpr uint32_t kQualBytes = 8u * 128u;
+	static constexpr uint32_t kQualBytes = 0u; // the general quality search runs when the copy area is free: its window lives there (7 words per lane)
 	static constexpr uint32_t kQueueBytes = kLaneQCap * 64u;
 	static constexpr uint32_t kRareBytes = 32u * 8u; // pairs waiting for the general path: pair index, len1 | len2 << 16
 	static constexpr uint32_t kWarpBytes = kCopyBytes + kQualBytes + kQueueBytes + kRareBytes;
@@ -90,7 +90,8 @@ __device__ __forceinline__ uint32_t lane_pack_word(uint32_t w, uint32_t& acch, u
 {
 	accl = __funnelshift_l((w & 0x02020202u) * kMulLo, accl, 4);
 	acch = __funnelshift_l((w & 0x04040404u) * kMulHi, acch, 4);
-	const uint32_t u = (w & 0x07070707u) | ((w >> 4) & 0xF8F8F8F8u); // byte k: index of byte k | index of byte k+1 << 4
+	uint32_t u; // byte k: index of byte k | index of byte k+1 << 4 = bit select (w & c) | ((w >> 4) & ~c), one LOP3
+	asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(u) : "r"(w), "r"(w >> 4), "r"(0x07070707u));
 	return prmt(kLutLo, kLutHi, prmt(u, 0u, 0x4420u)) ^ w;          // canonical bytes ^ bytes
 }
 
@@ -611,7 +612,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 	// ===== consumers: a warp claims the next staged tile of its CTA =====
 	const uint32_t wbase = smem_base + (uint32_t)S * stage_bytes + (uint32_t)warp * LaneSmem<NW>::kWarpBytes;
 	const uint32_t copy = wbase + 4u * (uint32_t)lane;                                      // word 0 of plane 0 of this lane
-	const uint32_t scr = wbase + LaneSmem<NW>::kCopyBytes + 4u * (uint32_t)lane;            // quality window
+	const uint32_t scr = copy;                                                              // quality window of the general search (after the scans)
 	const uint32_t queue = wbase + LaneSmem<NW>::kCopyBytes + LaneSmem<NW>::kQualBytes + 2u * (uint32_t)lane; // entry c at + 64c
 	const uint32_t rare = wbase + LaneSmem<NW>::kCopyBytes + LaneSmem<NW>::kQualBytes + LaneSmem<NW>::kQueueBytes;
 	const uint32_t thr_addr = smem_u32(F.thr);
@@ -644,6 +645,12 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 			len2 = A.len2[p];
 		}
 		bool plain = active && len1 == FULL && len2 == FULL;
+		if (active && A.qcut > 0) // the last qualities of both reads will be wanted at the end of this tile: start their way into L2 now
+		{
+			const size_t qoff = (size_t)p * A.stride + (size_t)(FULL - 16);
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(A.q1 + qoff));
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(A.q2 + qoff));
+		}
 
 		// ---- pack both reads from the staged rows, then hand the stage back ----
 		uint32_t f1h[NW], f1l[NW], f2h[NW], f2l[NW], r2l[NW];
