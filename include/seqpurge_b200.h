@@ -247,6 +247,8 @@ void spg_fq_close(spg_fq* fq);
 #define SPG_OPT_FULL_LEN 6        /* read length the kernel variant is chosen for (fast path for full-length pairs): -1 = automatic, 0 = general kernel only */
 #define SPG_OPT_KERNEL 7          /* thread layout of the read-length variants: 0 = automatic (one lane per pair where it applies), 1 = one warp per pair, 2 = as 0 */
 #define SPG_OPT_SEED_SCAN 8       /* lane-per-pair kernel: 1 (default) = exact-block filter in front of the adapter scans where the parameters allow it, 0 = every offset */
+#define SPG_OPT_ZERO_COPY_QUALS 9 /* slots (spg_submit): 1 (default) = when the lane-per-pair kernel runs, the quality planes are not copied; the kernel reads
+                                     the few quality bytes it needs from the pinned slot over PCIe. 0 = all four planes are copied */
 int spg_set_option(spg_ctx* ctx, int option, int value);
 
 /* Which trimming kernel the last launch of this context ran (bench.py reports it next to the roofline): writes the instantiation's name

@@ -235,6 +235,8 @@ struct Slot
 {
 	int dev = 0;
 	uint8_t* h_block = nullptr; // pinned: b1|q1|b2|q2|len1|len2
+	uint8_t* h_block_dev = nullptr; // the same memory as the slot's device sees it (mapped pinned memory)
+	bool zero_copy = false;     // last submit left the quality planes in the slot (see spg_submit)
 	uint8_t* d_block = nullptr;
 	spg_result* h_res = nullptr;
 	spg_result* d_res = nullptr;
@@ -271,6 +273,7 @@ struct spg_ctx
 	int tile_pairs = 0; // 0 = automatic
 	int stages = 0;     // 0 = automatic
 	long long launches = 0;
+	int zero_copy_quals = 1;           // SPG_OPT_ZERO_COPY_QUALS: slots leave the quality planes in pinned host memory when the lane kernel runs
 	int seed_scan = 1;                 // SPG_OPT_SEED_SCAN: 0 = the lane kernel evaluates every offset of the adapter scans (no pigeonhole filter)
 	int kernel_layout = 0;             // SPG_OPT_KERNEL: 0 automatic, 1 warp per pair only, 2 lane per pair where it applies
 	std::atomic<int> last_kernel{0};   // spg_last_kernel: layout * 100000 + NW * 1000 + FULL of the last trimming launch
@@ -416,15 +419,17 @@ int full_index(int nw, int full_len)
 // n_dev: optional device pointer to the actual pair count (<= n); n then sizes the grid only.
 // full_hint: read length most pairs of the batch are expected to have (0 = unknown); selects the kernel variant only.
 int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride, long long n,
-                spg_result* out, cudaStream_t stream, const int* n_dev = nullptr, int full_hint = -1)
+                spg_result* out, cudaStream_t stream, const int* n_dev = nullptr, int full_hint = -1, bool* lanes_query = nullptr, bool quals_on_host = false)
 {
-	if (n <= 0) return SPG_OK;
+	// lanes_query: only answer whether this launch would run the lane-per-pair kernel (nothing is launched)
+	if (n <= 0 && !lanes_query) return SPG_OK;
 	if (n > 0x7fffffffLL) return fail(ctx, SPG_ERR_PARAM, "at most 2^31-1 pairs per launch");
 	if (full_hint < 0) full_hint = ctx->max_len;
 	if (ctx->full_len >= 0) full_hint = ctx->full_len; // SPG_OPT_FULL_LEN
 	spg::KArgs a;
 	memset(&a, 0, sizeof(a));
 	a.n_dev = n_dev;
+	a.quals_on_host = quals_on_host ? 1 : 0;
 	a.b1 = b1;
 	a.q1 = q1;
 	a.b2 = b2;
@@ -520,6 +525,11 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	// the lane-per-pair kernel serves the read-length variants for everything but -ec (rows are edited in place), quality windows
 	// above 8 and presence fragments longer than the packed adapter planes; SPG_OPT_KERNEL 1 keeps the warp-per-pair kernel
 	const bool lanes = fi > 0 && ctx->kernel_layout != 1 && !p.ec && (p.qcut == 0 || p.qwin <= 8) && p.adapter_overlap <= ctx->a_size;
+	if (lanes_query)
+	{
+		*lanes_query = lanes;
+		return SPG_OK;
+	}
 	ctx->last_kernel.store(fi > 0 ? (lanes ? 2 : 1) * 100000 + nw * 1000 + full_hint : nw * 1000, std::memory_order_relaxed);
 	if (lanes)
 	{
@@ -678,6 +688,7 @@ int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, i
 		delete ctx;
 		return fail(nullptr, SPG_ERR_PARAM, err);
 	}
+	if (const char* e = getenv("SPG_ZERO_COPY_QUALS")) ctx->zero_copy_quals = atoi(e) ? 1 : 0;                                       // tuning runs only
 	if (const char* e = getenv("SPG_STAGES")) ctx->stages = std::max(0, std::min(atoi(e), (int)spg::kLaneStagesMax)); // tuning runs only
 	ctx->max_pairs = max_pairs;
 	ctx->max_len = max_len;
@@ -731,7 +742,8 @@ int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, i
 		Slot& sl = ctx->slots[(size_t)s];
 		sl.dev = s % n_devices;
 		CREATE_CUDA(cudaSetDevice(ctx->devs[(size_t)sl.dev].id));
-		CREATE_CUDA(cudaHostAlloc(&sl.h_block, ctx->block_bytes, cudaHostAllocPortable));
+		CREATE_CUDA(cudaHostAlloc(&sl.h_block, ctx->block_bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+		CREATE_CUDA(cudaHostGetDevicePointer((void**)&sl.h_block_dev, sl.h_block, 0));
 		CREATE_CUDA(cudaHostAlloc(&sl.h_res, (size_t)cap * sizeof(spg_result), cudaHostAllocPortable));
 		CREATE_CUDA(cudaMalloc(&sl.d_block, ctx->block_bytes));
 		CREATE_CUDA(cudaMalloc(&sl.d_res, (size_t)cap * sizeof(spg_result)));
@@ -775,7 +787,25 @@ int spg_submit(spg_ctx* ctx, int slot, int n_pairs)
 		const size_t rows = (size_t)n_pairs * ctx->stride;
 		const size_t lens = (size_t)((n_pairs + 7) / 8 * 8) * sizeof(uint16_t);
 		const size_t pb = ctx->plane_bytes;
-		if (n_pairs == ctx->max_pairs)
+		// The lane-per-pair kernel reads only the last qualities of a read (quality trimming): the quality planes then stay in the
+		// pinned slot and the kernel fetches the few sectors it needs over PCIe itself (zero copy: pinned memory is mapped into the
+		// device's address space), which cuts the bytes per pair on the link from 4L+4 to 2L+4 plus those sectors. Not with -qc
+		// (the statistics kernel reads every quality) and not for the other kernels (they stage whole quality rows).
+		bool zero_copy = false;
+		if (ctx->zero_copy_quals && !ctx->params.qc)
+		{
+			int qrc = launch_trim(ctx, d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->stride, n_pairs, nullptr, sl.stream, nullptr, -1, &zero_copy);
+			if (qrc != SPG_OK) return qrc;
+		}
+		sl.zero_copy = zero_copy;
+		if (zero_copy)
+		{
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block, sl.h_block, rows, cudaMemcpyHostToDevice, sl.stream));
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 2 * pb, sl.h_block + 2 * pb, rows, cudaMemcpyHostToDevice, sl.stream));
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb, sl.h_block + 4 * pb, lens, cudaMemcpyHostToDevice, sl.stream));
+			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb + ctx->len_bytes, sl.h_block + 4 * pb + ctx->len_bytes, lens, cudaMemcpyHostToDevice, sl.stream));
+		}
+		else if (n_pairs == ctx->max_pairs)
 		{
 			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block, sl.h_block, ctx->block_bytes, cudaMemcpyHostToDevice, sl.stream));
 		}
@@ -791,8 +821,10 @@ int spg_submit(spg_ctx* ctx, int slot, int n_pairs)
 			                    reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.stream);
 			if (qrc != SPG_OK) return qrc;
 		}
-		int rc = launch_trim(ctx, d, sl.d_block, sl.d_block + pb, sl.d_block + 2 * pb, sl.d_block + 3 * pb, reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb),
-		                     reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.d_res, sl.stream);
+		uint8_t* const q1 = zero_copy ? sl.h_block_dev + pb : sl.d_block + pb;
+		uint8_t* const q2 = zero_copy ? sl.h_block_dev + 3 * pb : sl.d_block + 3 * pb;
+		int rc = launch_trim(ctx, d, sl.d_block, q1, sl.d_block + 2 * pb, q2, reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb),
+		                     reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.d_res, sl.stream, nullptr, -1, nullptr, zero_copy);
 		if (rc != SPG_OK) return rc;
 		SPG_CUDA(ctx, cudaMemcpyAsync(sl.h_res, sl.d_res, (size_t)n_pairs * sizeof(spg_result), cudaMemcpyDeviceToHost, sl.stream));
 		if (ctx->params.ec) // edited rows come back in the slot
@@ -947,6 +979,7 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 		case SPG_OPT_GRID_CTAS_PER_SM: ctx->ctas_per_sm = value; return SPG_OK;
 		case SPG_OPT_FULL_LEN: ctx->full_len = value < 0 ? -1 : value; return SPG_OK;
 		case SPG_OPT_SEED_SCAN: ctx->seed_scan = value ? 1 : 0; return SPG_OK;
+		case SPG_OPT_ZERO_COPY_QUALS: ctx->zero_copy_quals = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_KERNEL:
 			if (value < 0 || value > 2) return fail(ctx, SPG_ERR_PARAM, "kernel layout must be 0 (automatic), 1 (warp per pair) or 2 (lane per pair)");
 			ctx->kernel_layout = value;

@@ -75,6 +75,7 @@ struct KArgs
 	uint32_t a1pass, a2pass; // bit j: a full-window comparison (all of amask) with j mismatches passes
 	int a1maxmm, a2maxmm;    // the same as a limit: most mismatches with which a full window passes (-1: never); only valid if full_ok
 	int full_ok;             // adapters without N in their first a_size bases and every pass set of steps 2/3 an interval 0..k of mismatches
+	int quals_on_host;       // lane kernel: q1 / q2 point into mapped pinned host memory (zero copy): no speculative prefetches over PCIe
 	int seed_ok;             // lane kernel: every passing window of steps 2/3 has fewer mismatches than complete 4-base adapter blocks (and full_ok)
 	uint16_t a1off[20];      // lane kernel: byte offset of the base-indicator plane (A,C,G,T -> 0..3 times (NW+1)*128) of adapter position i
 	uint16_t a2off[20];

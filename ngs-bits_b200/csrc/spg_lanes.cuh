@@ -390,13 +390,24 @@ __device__ __forceinline__ int lane_trim_quality5(const KArgs& A, const uint8_t*
 {
 	const int cutb = A.qcut + A.qoff, thrb = A.qthr + 5 * A.qoff;
 	if (n < 16 || cutb < 1 || cutb > 127) return -1;
+	// two aligned 16-byte loads cover the 16 bytes wherever they start (one request per half sector: the quality planes may live in
+	// pinned host memory, where every load instruction is a read over PCIe); the second one is not needed for an aligned start
 	const uintptr_t a = (uintptr_t)qrow + (uintptr_t)(n - 16);
-	const uint32_t boff = (uint32_t)(a & 3u);
-	const uint32_t* wp = reinterpret_cast<const uint32_t*>(a - boff);
+	const uint32_t off = (uint32_t)(a & 15u);
+	const uint4* wp = reinterpret_cast<const uint4*>(a - off);
+	const uint4 lo = __ldg(wp);
+	uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+	if (off) hi = __ldg(wp + 1);
+	// words off/4 .. off/4+4 of the eight, then the byte shift inside a word
+	const bool s2 = off & 8u, s1 = off & 4u;
+	const uint32_t x0 = s2 ? lo.z : lo.x, x1 = s2 ? lo.w : lo.y, x2 = s2 ? hi.x : lo.z, x3 = s2 ? hi.y : lo.w, x4 = s2 ? hi.z : hi.x, x5 = s2 ? hi.w : hi.y;
 	uint32_t w[5];
-#pragma unroll
-	for (int k = 0; k < 4; ++k) w[k] = __ldg(wp + k);
-	w[4] = boff ? __ldg(wp + 4) : 0u; // starts at the read's end when the window is word aligned
+	w[0] = s1 ? x1 : x0;
+	w[1] = s1 ? x2 : x1;
+	w[2] = s1 ? x3 : x2;
+	w[3] = s1 ? x4 : x3;
+	w[4] = s1 ? x5 : x4;
+	const uint32_t boff = off & 3u;
 	uint32_t v[4];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) v[k] = __funnelshift_r(w[k], w[k + 1], 8u * boff); // bytes of positions n-16+4k ..
@@ -645,7 +656,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 			len2 = A.len2[p];
 		}
 		bool plain = active && len1 == FULL && len2 == FULL;
-		if (active && A.qcut > 0) // the last qualities of both reads will be wanted at the end of this tile: start their way into L2 now
+		if (active && A.qcut > 0 && !A.quals_on_host) // the last qualities of both reads will be wanted at the end of this tile: start their way into L2 now
 		{
 			const size_t qoff = (size_t)p * A.stride + (size_t)(FULL - 16);
 			asm volatile("prefetch.global.L2 [%0];" ::"l"(A.q1 + qoff));
