@@ -251,6 +251,8 @@ void spg_fq_close(spg_fq* fq);
                                      the few quality bytes it needs from the pinned slot over PCIe. 0 = all four planes are copied */
 int spg_set_option(spg_ctx* ctx, int option, int value);
 
+int spg_get_option(spg_ctx* ctx, int option, int* value);
+
 /* Which trimming kernel the last launch of this context ran (bench.py reports it next to the roofline): writes the instantiation's name
    into name[cap]; returns layout * 100000 + NW * 1000 + FULL (layout 0: general kernel, 1: warp per pair, 2: lane per pair), 0 before
    the first launch. */

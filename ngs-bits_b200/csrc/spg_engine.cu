@@ -1010,6 +1010,24 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 	}
 }
 
+int spg_get_option(spg_ctx* ctx, int option, int* value)
+{
+	if (!ctx || !value) return SPG_ERR_PARAM;
+	switch (option)
+	{
+		case SPG_OPT_FORCE_BYTEWISE: *value = ctx->force_bytewise; return SPG_OK;
+		case SPG_OPT_GRID_CTAS_PER_SM: *value = ctx->ctas_per_sm; return SPG_OK;
+		case SPG_OPT_MIN_BLOCKS: *value = ctx->min_blocks; return SPG_OK;
+		case SPG_OPT_TILE_PAIRS: *value = ctx->tile_pairs; return SPG_OK;
+		case SPG_OPT_STAGES: *value = ctx->stages; return SPG_OK;
+		case SPG_OPT_FULL_LEN: *value = ctx->full_len; return SPG_OK;
+		case SPG_OPT_KERNEL: *value = ctx->kernel_layout; return SPG_OK;
+		case SPG_OPT_SEED_SCAN: *value = ctx->seed_scan; return SPG_OK;
+		case SPG_OPT_ZERO_COPY_QUALS: *value = ctx->zero_copy_quals; return SPG_OK;
+		default: return fail(ctx, SPG_ERR_PARAM, "unknown option");
+	}
+}
+
 int spg_last_kernel(spg_ctx* ctx, char* name, int cap)
 {
 	if (!ctx) return SPG_ERR_PARAM;

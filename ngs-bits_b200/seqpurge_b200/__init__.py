@@ -109,6 +109,8 @@ _lib.spg_destroy.argtypes = [C.c_void_p]
 _lib.spg_destroy.restype = None
 _lib.spg_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
 _lib.spg_set_option.restype = C.c_int
+_lib.spg_get_option.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+_lib.spg_get_option.restype = C.c_int
 _lib.spg_last_kernel.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
 _lib.spg_last_kernel.restype = C.c_int
 _lib.spg_launch_count.argtypes = [C.c_void_p]
@@ -290,6 +292,16 @@ class Engine:
 
     def set_option(self, option, value):
         self._check(_lib.spg_set_option(self._h, option, value), "spg_set_option")
+
+    def get_option(self, option):
+        v = C.c_int(0)
+        self._check(_lib.spg_get_option(self._h, option, C.byref(v)), "spg_get_option")
+        return v.value
+
+    @property
+    def zero_copy_quals(self):
+        """True if submitted slots leave their quality planes in pinned host memory when the lane-per-pair kernel runs."""
+        return bool(self.get_option(OPT_ZERO_COPY_QUALS))
 
     @property
     def launch_count(self):

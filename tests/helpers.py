@@ -264,3 +264,55 @@ def random_batch(n, L, seed, insert_mean=None, insert_sd=None, error_rate=0.01, 
             reads.append((seq.tobytes(), q.tobytes()))
         b.set_pair(i, reads[0][0], reads[0][1], reads[1][0], reads[1][1])
     return b
+
+
+def synth_batch_numpy(n, L, seed=1, stride=None, insert_mean=250.0, insert_sd=80.0, insert_min=1, insert_max=2000, error_rate=0.001, n_rate=1e-4,
+                      lowq_tail_mean=3.0, n_run_rate=0.0, binned_quals=False, a1=DEFAULT_A1, a2=DEFAULT_A2):
+    """Vectorised numpy generator of the synthetic model of SURVEY.md section 8d (the parameters of seqpurge_b200.SynthConfig): fragment
+    of insert ~ N(mu, sigma) clipped, read 1 = fragment + adapter 1 + random filler, read 2 = revcomp(fragment) + adapter 2 + filler,
+    i.i.d. substitutions and N, qualities 'I' with a geometric low-quality tail ('#'), optional N runs and binned qualities. The same
+    distribution as the device generator, not the same random stream (used where no CUDA library may be loaded: bench.py's CPU arm)."""
+    rng = np.random.default_rng(seed)
+    if stride is None:
+        stride = (L + 1) // 2 * 2
+    b = Batch(n, stride)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    comp = np.zeros(256, np.uint8)
+    for x, y in zip(b"ACGTN", b"TGCAN"):
+        comp[x] = y
+    ins = np.clip(np.rint(rng.normal(insert_mean, insert_sd, n)), insert_min, insert_max).astype(np.int64)
+    ins = np.minimum(ins, 2 * L)  # longer fragments: the two reads do not overlap, their bases are independent either way
+    frag = acgt[rng.integers(0, 4, (n, 2 * L))]
+    col = np.arange(L)[None, :]
+    ad1 = np.concatenate([np.frombuffer(a1.encode(), np.uint8), acgt[rng.integers(0, 4, L)]])[: L]
+    ad2 = np.concatenate([np.frombuffer(a2.encode(), np.uint8), acgt[rng.integers(0, 4, L)]])[: L]
+    rel = col - ins[:, None]  # position inside adapter + filler where the read runs past the fragment
+    inside = rel < 0
+    filler = acgt[rng.integers(0, 4, (n, L))]
+    r1 = np.where(inside, frag[:, :L], np.where(rel < len(a1), ad1[np.clip(rel, 0, L - 1)], filler))
+    idx = np.clip(ins[:, None] - 1 - col, 0, 2 * L - 1)
+    r2 = np.where(inside, comp[np.take_along_axis(frag, idx, axis=1)], np.where(rel < len(a2), ad2[np.clip(rel, 0, L - 1)], filler[:, ::-1]))
+    for r in (r1, r2):
+        err = rng.random((n, L)) < error_rate
+        r[err] = acgt[rng.integers(0, 4, int(err.sum()))]
+        r[rng.random((n, L)) < n_rate] = 78
+        if n_run_rate > 0:
+            rows = np.nonzero(rng.random(n) < n_run_rate)[0]
+            for i in rows:
+                st = int(rng.integers(0, L - 12))
+                r[i, st : st + int(rng.integers(7, 12))] = 78
+    hi, lo = (ord("F"), ord("#")) if binned_quals else (ord("I"), ord("#"))
+    for r, q, ln in ((r1, b.quals1, b.len1), (r2, b.quals2, b.len2)):
+        qq = np.full((n, L), hi, np.uint8)
+        if binned_quals:
+            u = rng.random((n, L))
+            qq[u < 0.08] = ord(":")
+            qq[u < 0.02] = ord(",")
+        if lowq_tail_mean > 0:
+            t = rng.geometric(1.0 / (1.0 + lowq_tail_mean), n) - 1
+            qq[col >= (L - t)[:, None]] = lo
+        q[:n, :L] = qq
+        ln[:n] = L
+    b.bases1[:n, :L] = r1
+    b.bases2[:n, :L] = r2
+    return b
