@@ -209,6 +209,7 @@ def main():
     ap.add_argument("--e2e-pairs", type=int, default=1_000_000, help="pairs per pinned slot for the end-to-end measurement")
     ap.add_argument("--e2e-slots", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--only", default="", help="profiling aid: measure just this config (C2..C5) device-resident and print its result")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -377,6 +378,11 @@ def main():
 
     B = (args.pairs_per_step + 7) // 8 * 8
     pool_n = max(1, min(args.pool, args.steps + args.warmup))
+    if args.only:
+        r, _, _ = measure(args.only, args.steps, args.warmup, B if CONFIGS[args.only]["read_len"] <= 160 else B // 2, pool_n, True)
+        if rank == 0:
+            emit(r)
+        return 0
     headline, pool, eng0 = measure("C2", args.steps, args.warmup, B, pool_n, True)
     L0, stride0 = head["read_len"], row_stride(head["read_len"])
 

@@ -249,6 +249,7 @@ void spg_fq_close(spg_fq* fq);
 #define SPG_OPT_SEED_SCAN 8       /* lane-per-pair kernel: 1 (default) = exact-block filter in front of the adapter scans where the parameters allow it, 0 = every offset */
 #define SPG_OPT_ZERO_COPY_QUALS 9 /* slots (spg_submit): 1 (default) = when the lane-per-pair kernel runs, the quality planes are not copied; the kernel reads
                                      the few quality bytes it needs from the pinned slot over PCIe. 0 = all four planes are copied */
+#define SPG_OPT_N_LANES 10        /* lane-per-pair kernel: 1 (default) = pairs with N take its N-aware path, 0 = the warp-cooperative general path */
 int spg_set_option(spg_ctx* ctx, int option, int value);
 
 int spg_get_option(spg_ctx* ctx, int option, int* value);

@@ -113,7 +113,9 @@ bool build_tables(const spg_params& p, int a_size, HostTables& t, std::string& e
 				return false;
 			}
 			cell[(size_t)count * spg::kRankDim + n] = v;
-			if (!(v > p.mep)) ps.push_back(v);
+			// an offset can only become the best one with p <= mep AND p < best_p, which starts at 1.0 (AnalysisWorker.cpp:138,261):
+			// a cell with p == 1.0 never wins, whatever -mep says
+			if (!(v > p.mep) && v < 1.0) ps.push_back(v);
 		}
 	}
 	std::sort(ps.begin(), ps.end());
@@ -129,7 +131,7 @@ bool build_tables(const spg_params& p, int a_size, HostTables& t, std::string& e
 		for (int n = 0; n <= count; ++n)
 		{
 			double v = cell[(size_t)count * spg::kRankDim + n];
-			if (v > p.mep) continue;
+			if (v > p.mep || !(v < 1.0)) continue;
 			t.ranktab[(size_t)count * spg::kRankDim + n] = (uint16_t)(std::lower_bound(ps.begin(), ps.end(), v) - ps.begin());
 		}
 	}
@@ -273,6 +275,7 @@ struct spg_ctx
 	int tile_pairs = 0; // 0 = automatic
 	int stages = 0;     // 0 = automatic
 	long long launches = 0;
+	int n_lanes = 1;                   // SPG_OPT_N_LANES: pairs with N go through the lane kernel's N-aware path (0: warp-cooperative general path)
 	int zero_copy_quals = 1;           // SPG_OPT_ZERO_COPY_QUALS: slots leave the quality planes in pinned host memory when the lane kernel runs
 	int seed_scan = 1;                 // SPG_OPT_SEED_SCAN: 0 = the lane kernel evaluates every offset of the adapter scans (no pigeonhole filter)
 	int kernel_layout = 0;             // SPG_OPT_KERNEL: 0 automatic, 1 warp per pair only, 2 lane per pair where it applies
@@ -430,6 +433,7 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	memset(&a, 0, sizeof(a));
 	a.n_dev = n_dev;
 	a.quals_on_host = quals_on_host ? 1 : 0;
+	a.n_lanes = ctx->n_lanes;
 	a.b1 = b1;
 	a.q1 = q1;
 	a.b2 = b2;
@@ -689,6 +693,7 @@ int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, i
 		return fail(nullptr, SPG_ERR_PARAM, err);
 	}
 	if (const char* e = getenv("SPG_ZERO_COPY_QUALS")) ctx->zero_copy_quals = atoi(e) ? 1 : 0;                                       // tuning runs only
+	if (const char* e = getenv("SPG_N_LANES")) ctx->n_lanes = atoi(e) ? 1 : 0;                                                        // tuning runs only
 	if (const char* e = getenv("SPG_STAGES")) ctx->stages = std::max(0, std::min(atoi(e), (int)spg::kLaneStagesMax)); // tuning runs only
 	ctx->max_pairs = max_pairs;
 	ctx->max_len = max_len;
@@ -980,6 +985,7 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 		case SPG_OPT_FULL_LEN: ctx->full_len = value < 0 ? -1 : value; return SPG_OK;
 		case SPG_OPT_SEED_SCAN: ctx->seed_scan = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_ZERO_COPY_QUALS: ctx->zero_copy_quals = value ? 1 : 0; return SPG_OK;
+		case SPG_OPT_N_LANES: ctx->n_lanes = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_KERNEL:
 			if (value < 0 || value > 2) return fail(ctx, SPG_ERR_PARAM, "kernel layout must be 0 (automatic), 1 (warp per pair) or 2 (lane per pair)");
 			ctx->kernel_layout = value;
@@ -1024,6 +1030,7 @@ int spg_get_option(spg_ctx* ctx, int option, int* value)
 		case SPG_OPT_KERNEL: *value = ctx->kernel_layout; return SPG_OK;
 		case SPG_OPT_SEED_SCAN: *value = ctx->seed_scan; return SPG_OK;
 		case SPG_OPT_ZERO_COPY_QUALS: *value = ctx->zero_copy_quals; return SPG_OK;
+		case SPG_OPT_N_LANES: *value = ctx->n_lanes; return SPG_OK;
 		default: return fail(ctx, SPG_ERR_PARAM, "unknown option");
 	}
 }

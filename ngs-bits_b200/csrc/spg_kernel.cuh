@@ -76,6 +76,7 @@ struct KArgs
 	int a1maxmm, a2maxmm;    // the same as a limit: most mismatches with which a full window passes (-1: never); only valid if full_ok
 	int full_ok;             // adapters without N in their first a_size bases and every pass set of steps 2/3 an interval 0..k of mismatches
 	int quals_on_host;       // lane kernel: q1 / q2 point into mapped pinned host memory (zero copy): no speculative prefetches over PCIe
+	int n_lanes;             // lane kernel: pairs with N take the N-aware lane path (0: the general path, SPG_OPT_N_LANES)
 	int seed_ok;             // lane kernel: every passing window of steps 2/3 has fewer mismatches than complete 4-base adapter blocks (and full_ok)
 	uint16_t a1off[20];      // lane kernel: byte offset of the base-indicator plane (A,C,G,T -> 0..3 times (NW+1)*128) of adapter position i
 	uint16_t a2off[20];
@@ -898,6 +899,7 @@ struct FullTab
 	static constexpr int QF = full_qf(FULL) < NW ? full_qf(FULL) : NW;
 	static constexpr int NT = NW - QF > 0 ? NW - QF : 1;
 	int16_t thr[32 * NW]; // [o]: most mismatches with which insert offset o survives the pre-filter (mmin), -1: never
+	int16_t thr_env[32 * NW]; // [o]: the largest thr of any overlap of at most FULL-o compared bases (reads with N: fewer positions are compared)
 	// adapter scans: a window of cnt compared bases is "x << (32-cnt)" (a multiplication by .x = 2^(32-cnt), which runs on the FMA
 	// pipe) and passes with at most .y mismatches (-1: never, e.g. no base left or a round that starts in front of the read)
 	int2 r1tail[NT][32];  // read-1 scan, round QF+t, lane
@@ -918,6 +920,16 @@ __device__ __forceinline__ void full_tab_init(const KArgs& A, const SmemTables& 
 		int t = -1;
 		if (o >= 1 && tot > 0) t = max(tot - (int)T.mmin[tot], -1);
 		F.thr[o] = (int16_t)t;
+	}
+	if (tid == 0) // running maximum over growing overlaps (o descending); a few hundred steps once per CTA
+	{
+		int best = -1;
+		for (int o = 32 * NW - 1; o >= 0; --o)
+		{
+			const int tot = FULL - o;
+			if (o >= 1 && tot > 0) best = max(best, max(tot - (int)T.mmin[tot], -1));
+			F.thr_env[o] = (int16_t)(o >= 1 && tot > 0 ? best : -1);
+		}
 	}
 	for (int i = tid; i < 32 * (NW - QF); i += nthreads)
 	{

@@ -501,6 +501,349 @@ __device__ __noinline__ int lane_trim_quality(const KArgs& A, const uint8_t* qro
 	return res;
 }
 
+// FastqEntry::trimN (src/cppNGS/FastqFileStream.cpp:89-117) on the forward N plane of one read: first run of num_n consecutive N
+// that lies inside the first `count` bases; returns the new length
+template <int NW>
+__device__ __forceinline__ int lane_trim_n(const uint32_t* npl, int count, int num_n)
+{
+	if (count < num_n) return count;
+	uint32_t run[NW]; // bit s: positions s .. s+k are all N
+	bool any = false;
+#pragma unroll
+	for (int w = 0; w < NW; ++w)
+	{
+		run[w] = npl[w];
+		any |= run[w] != 0;
+	}
+	if (!any) return count;
+	for (int k = 1; k < num_n; ++k) // AND with the plane shifted right by k bits
+	{
+		const int wo = k >> 5;
+#pragma unroll
+		for (int w = 0; w < NW; ++w)
+		{
+			uint32_t lo = 0, hi = 0;
+#pragma unroll
+			for (int u = 0; u < NW; ++u)
+			{
+				if (u == w + wo) lo = npl[u];
+				if (u == w + wo + 1) hi = npl[u];
+			}
+			run[w] &= __funnelshift_r(lo, hi, k);
+		}
+	}
+	int s = -1;
+#pragma unroll
+	for (int w = NW - 1; w >= 0; --w)
+		if (run[w]) s = 32 * w + __ffs((int)run[w]) - 1;
+	return (s >= 0 && s <= count - num_n) ? s : count;
+}
+
+// ---- lengths from the three steps, quality trimming, [N trimming,] the record: the end of a pair's work, one pair per lane --------------------
+// key: best insert candidate or kNoKey; fwd / rev: adapter-only offsets or -1. n1pl / n2pl: forward N planes of the two reads (lanes that may
+// hold N), or null. All lanes of the warp call it together; only lanes with `plain` write a record.
+template <int FULL, int NW = 1>
+__device__ __forceinline__ void lane_finish(const KArgs& A, uint32_t p, bool plain, uint32_t key, int fwd, int rev, const uint32_t* n1pl, const uint32_t* n2pl, uint32_t scr)
+{
+	int n1 = FULL, n2 = FULL, best_offset = -1;
+	uint32_t flags = 0;
+	if (key != kNoKey) // insert hit (AnalysisWorker.cpp:269-302)
+	{
+		best_offset = (int)(key & 0xFFFFu);
+		n1 = n2 = FULL - best_offset;
+		flags |= SPG_F_INSERT;
+	}
+	else if (fwd >= 0 || rev >= 0) // adapter-only hit (:410-426)
+	{
+		flags |= SPG_F_ADAPTER;
+		if (fwd >= 0) n1 = fwd;
+		if (rev >= 0) n2 = rev;
+		if (fwd < 0) n1 = min(n1, rev);
+		if (rev < 0) n2 = min(n2, fwd);
+	}
+	if (A.qcut > 0) // :430-434
+	{
+		const size_t goff = (size_t)p * A.stride;
+		int t1 = -1, t2 = -1;
+		if (A.qwin == 5 && plain) // 16 qualities in registers, twelve window starts at a time from the 3' end
+		{
+			int e1 = n1, e2 = n2;
+			for (int k = 0; k < 8; ++k)
+			{
+				if (t1 < 0 && e1 >= 16) t1 = lane_trim_quality5(A, A.q1 + goff, e1);
+				if (t2 < 0 && e2 >= 16) t2 = lane_trim_quality5(A, A.q2 + goff, e2);
+				e1 -= 12;
+				e2 -= 12;
+				if (!((t1 < 0 && e1 >= 16) || (t2 < 0 && e2 >= 16))) break;
+			}
+		}
+		if (__any_sync(kFull, plain && t1 < 0)) t1 = lane_trim_quality(A, A.q1 + goff, n1, plain && t1 < 0, scr, t1);
+		if (__any_sync(kFull, plain && t2 < 0)) t2 = lane_trim_quality(A, A.q2 + goff, n2, plain && t2 < 0, scr, t2);
+		if (t1 < n1) flags |= SPG_F_Q1;
+		if (t2 < n2) flags |= SPG_F_Q2;
+		n1 = t1;
+		n2 = t2;
+	}
+	if (A.ncut > 0 && n1pl != nullptr && plain) // :437-441, FastqEntry::trimN: the first run of ncut N inside the (trimmed) read cuts it there
+	{
+		const int t1 = lane_trim_n<NW>(n1pl, n1, A.ncut), t2 = lane_trim_n<NW>(n2pl, n2, A.ncut);
+		if (t1 < n1) flags |= SPG_F_N1;
+		if (t2 < n2) flags |= SPG_F_N2;
+		n1 = t1;
+		n2 = t2;
+	}
+	if (plain)
+	{
+		uint2 rec;
+		rec.x = (uint32_t)n1 | ((uint32_t)n2 << 16);
+		rec.y = ((uint32_t)best_offset & 0xFFFFu) | (flags << 16);
+		*reinterpret_cast<uint2*>(A.out + p) = rec;
+	}
+}
+
+// =========================================================================================================================================
+// Pairs with N. About 3 % of the pairs of a typical run hold an N somewhere; the warp-cooperative general path costs six times a
+// lane's work for each of them. They are collected instead (with everything else that left the main path) and 32 at a time go through
+// the same lane-per-pair steps in an N-aware form: rows read from global memory (they are no longer staged), a third plane for N,
+// N positions masked out of every comparison, thresholds that hold for any number of remaining positions. A pair that is not
+// "two reads of FULL bases made of A/C/G/T/N" still ends in the general path.
+// =========================================================================================================================================
+constexpr uint32_t kMulN = (1u << 28) | (1u << 19) | (1u << 10) | (1u << 1); // bit 3 of the four bytes ('N' is the only one of ACGTN that has it) -> top nibble
+constexpr uint32_t kLutHiN = 0x474EFF54u;                                     // as kLutHi, with index 6 -> 'N'
+
+// 32 bits of a plane held in registers, from bit pos (0 <= pos < 32 NW)
+template <int NW>
+__device__ __forceinline__ uint32_t lane_reg_extract(const uint32_t (&pl)[NW], int pos)
+{
+	const int wi = pos >> 5;
+	uint32_t lo = 0, hi = 0;
+#pragma unroll
+	for (int w = 0; w < NW; ++w)
+		if (wi == w)
+		{
+			lo = pl[w];
+			hi = (w + 1 < NW) ? pl[w + 1 < NW ? w + 1 : 0] : 0u;
+		}
+	return __funnelshift_r(lo, hi, pos);
+}
+
+// Packs one read from its row in GLOBAL memory (2-byte aligned, FULL bases) into the reversed accumulators of the hi, lo and N plane
+// (see lane_pack_rows); returns != 0 if a byte is not one of A/C/G/T/N.
+template <int NW, int FULL>
+__device__ __noinline__ uint32_t lane_pack_global(const uint8_t* row, uint32_t* acch, uint32_t* accl, uint32_t* accn)
+{
+	constexpr int NWRD = (FULL + 2 + 3) / 4;
+	const uintptr_t ra = (uintptr_t)row;
+	const int odd = (int)(ra & 2u);
+	const uint32_t* wp = reinterpret_cast<const uint32_t*>(ra & ~(uintptr_t)3);
+	uint32_t bad = 0;
+#pragma unroll 1
+	for (int g = 0; g < NW; ++g)
+	{
+		uint32_t ah = 0, al = 0, an = 0;
+		uint32_t w[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k) w[k] = (8 * g + k < NWRD) ? __ldg(wp + 8 * g + k) : 0u; // words behind the row add empty nibbles
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+		{
+			const int lo = 4 * (8 * g + k) - odd; // position of the word's first byte
+			al = __funnelshift_l((w[k] & 0x02020202u) * kMulLo, al, 4);
+			ah = __funnelshift_l((w[k] & 0x04040404u) * kMulHi, ah, 4);
+			an = __funnelshift_l((w[k] & 0x08080808u) * kMulN, an, 4);
+			// canonical byte by the low three bits (N included); the selector's spare bit takes the byte's own bit 7, see kLutLo
+			uint32_t u;
+			asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(u) : "r"(w[k]), "r"(w[k] >> 4), "r"(0x87878787u));
+			uint32_t d = prmt(kLutLo, kLutHiN, prmt(u, 0u, 0x4420u)) ^ w[k];
+			const int first = max(0, -lo), last = min(4, FULL - lo); // bytes [first, last) of this word belong to the read
+			uint32_t m = 0;
+			if (last > first) m = (last >= 4 ? 0xFFFFFFFFu : ((1u << (8 * last)) - 1u)) & ~((1u << (8 * first)) - 1u);
+			bad |= d & m;
+		}
+		acch[g] = ah;
+		accl[g] = al;
+		accn[g] = an;
+	}
+	return bad;
+}
+
+// exact counts of insert offset o with N positions left out (AnalysisWorker.cpp:151-168): mismatches and compared positions
+template <int NW, int FULL>
+__device__ __forceinline__ void lane_exact_mm_n(int o, const uint32_t (&f1h)[NW], const uint32_t (&f1l)[NW], const uint32_t (&n1)[NW], const uint32_t (&r2h)[NW],
+                                                const uint32_t (&r2l)[NW], const uint32_t (&n2r)[NW], int& mm, int& tot)
+{
+	mm = 0;
+	tot = 0;
+#pragma unroll
+	for (int k = 0; k < NW; ++k)
+	{
+		const int n = FULL - o - 32 * k;
+		if (n > 0)
+		{
+			const uint32_t sh = lane_reg_extract<NW>(r2h, o + 32 * k), sl = lane_reg_extract<NW>(r2l, o + 32 * k), sn = lane_reg_extract<NW>(n2r, o + 32 * k);
+			const uint32_t valid = low_bits(n) & ~(sn | n1[k]);
+			mm += __popc((~(sh ^ f1h[k]) | (sl ^ f1l[k])) & valid);
+			tot += __popc(valid);
+		}
+	}
+}
+
+// lane_candidate_key with N positions of the reads left out of the adapter fragments
+template <int NW, int FULL>
+__device__ __forceinline__ uint32_t lane_candidate_key_n(const KArgs& A, int o, int m, int mm, const uint32_t (&f1h)[NW], const uint32_t (&f1l)[NW], const uint32_t (&n1)[NW],
+                                                         const uint32_t (&r2h)[NW], const uint32_t (&r2l)[NW], const uint32_t (&n2r)[NW])
+{
+	int n = m, mis = mm, cnt = m + mm;
+	while (cnt >= kRankDim)
+	{
+		n >>= 1;
+		mis >>= 1;
+		cnt = n + mis;
+	}
+	const uint32_t rank = __ldg(&A.ranktab[cnt * kRankDim + n]);
+	if (rank == 0xFFFFu) return kNoKey;
+	const int alen = min(A.ao, o);
+	const int pos = FULL - o;
+	const uint32_t v1h = lane_reg_extract<NW>(f1h, pos), v1l = lane_reg_extract<NW>(f1l, pos), v1n = lane_reg_extract<NW>(n1, pos);
+	const uint32_t e2h = lane_reg_extract<NW>(r2h, o - alen), e2l = lane_reg_extract<NW>(r2l, o - alen), e2n = lane_reg_extract<NW>(n2r, o - alen);
+	const uint32_t v2h = __brev(e2h) >> (32 - alen), v2l = __brev(e2l) >> (32 - alen), v2n = __brev(e2n) >> (32 - alen);
+	const uint32_t val1 = low_bits(alen) & ~A.a1n & ~v1n, val2 = low_bits(alen) & ~A.a2n & ~v2n;
+	const int mm1 = __popc(((v1h ^ A.a1h) | (v1l ^ A.a1l)) & val1), m1 = __popc(val1) - mm1;
+	const int mm2 = __popc(((v2h ^ A.a2h) | (v2l ^ A.a2l)) & val2), m2 = __popc(val2) - mm2;
+	if (o < 10)
+	{
+		const int max_mm = o < 3 ? 0 : (o < 6 ? 1 : 2);
+		if (!(mm1 <= max_mm || mm2 <= max_mm)) return kNoKey;
+	}
+	else
+	{
+		const double p1 = __ldg(&A.psmall[(m1 + mm1) * (A.ao + 1) + m1]);
+		const double p2 = __ldg(&A.psmall[(m2 + mm2) * (A.ao + 1) + m2]);
+		if (__dmul_rn(p1, p2) > A.mep) return kNoKey;
+	}
+	return (rank << 16) | (uint32_t)o;
+}
+
+// adapter-only scan of a read that may hold N: every offset, N positions left out of the window (the pass table is indexed by the
+// number of compared bases, as in adapter_scan_rounds)
+template <int NW, int FULL>
+__device__ __forceinline__ int lane_adapter_scan_n(const KArgs& A, const SmemTables& T, const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], const uint32_t (&fn)[NW], uint32_t ah,
+                                                   uint32_t al, uint32_t an)
+{
+	uint32_t best = 0xFFFFFFFFu;
+#pragma unroll 1
+	for (int r = 0; r < 32; ++r)
+	{
+#pragma unroll
+		for (int q = NW - 1; q >= 0; --q)
+		{
+			const int cnt = min(A.a_size, FULL - 32 * q - r);
+			if (cnt > 0)
+			{
+				const uint32_t sh = __funnelshift_r(fh[q], (q + 1 < NW) ? fh[q + 1 < NW ? q + 1 : 0] : 0u, r);
+				const uint32_t sl = __funnelshift_r(fl[q], (q + 1 < NW) ? fl[q + 1 < NW ? q + 1 : 0] : 0u, r);
+				const uint32_t sn = __funnelshift_r(fn[q], (q + 1 < NW) ? fn[q + 1 < NW ? q + 1 : 0] : 0u, r);
+				const uint32_t valid = low_bits(cnt) & ~an & ~sn;
+				const uint32_t x = (sh ^ ah) | (sl ^ al);
+				if ((T.passM[__popc(valid)] >> __popc(x & valid)) & 1u) best = min(best, (uint32_t)(32 * q + r));
+			}
+		}
+	}
+	return (int)best;
+}
+
+// up to 32 collected pairs (entry e: pair index, len1 | len2 << 16 at list + 8e), one per lane. Returns the lanes whose pair still
+// needs the general path.
+template <int NW, int FULL>
+__device__ __noinline__ uint32_t lane_tile_n(const KArgs& A, const SmemTables& T, const FullTab<NW, FULL>& F, uint32_t list, int n_entries, uint32_t queue, uint32_t scr, int lane)
+{
+	uint32_t p = 0;
+	bool plain = false;
+	if (lane < n_entries)
+	{
+		const uint2 ent = lds_v2(list + 8u * (uint32_t)lane);
+		p = ent.x;
+		plain = (ent.y & 0xFFFFu) == (uint32_t)FULL && (ent.y >> 16) == (uint32_t)FULL;
+	}
+	const bool member = lane < n_entries;
+	uint32_t f1h[NW], f1l[NW], n1[NW], f2h[NW], f2l[NW], n2[NW], r2h[NW], r2l[NW], n2r[NW];
+	{
+		uint32_t acch[NW], accl[NW], accn[NW];
+		const size_t goff = (size_t)p * A.stride;
+		const uint32_t odd1 = (uint32_t)((uintptr_t)(A.b1 + goff) & 2u), odd2 = (uint32_t)((uintptr_t)(A.b2 + goff) & 2u);
+		uint32_t bad = 0;
+		if (plain) bad = lane_pack_global<NW, FULL>(A.b1 + goff, acch, accl, accn);
+		lane_forward<NW, FULL>(acch, odd1, f1h);
+		lane_forward<NW, FULL>(accl, odd1, f1l);
+		lane_forward<NW, FULL>(accn, odd1, n1);
+		if (plain) bad |= lane_pack_global<NW, FULL>(A.b2 + goff, acch, accl, accn);
+		lane_forward<NW, FULL>(acch, odd2, f2h);
+		lane_forward<NW, FULL>(accl, odd2, f2l);
+		lane_forward<NW, FULL>(accn, odd2, n2);
+		lane_reversed<NW, FULL>(acch, odd2, r2h);
+		lane_reversed<NW, FULL>(accl, odd2, r2l);
+		lane_reversed<NW, FULL>(accn, odd2, n2r);
+		plain = plain && bad == 0;
+	}
+	// ---- step 1: the pre-filter counts lo-plane differences at positions where neither read holds an N and compares with the
+	// largest limit of any overlap of at most that many bases (F.thr_env): the N positions only shrink the set of compared positions
+	int nq = 0;
+	{
+		uint32_t v1[NW]; // lo plane and "not N" of read 1
+#pragma unroll
+		for (int w = 0; w < NW; ++w) v1[w] = ~n1[w];
+#pragma unroll 1
+		for (int r = 0; r < 32; ++r)
+		{
+			uint32_t sv[NW], svn[NW];
+#pragma unroll
+			for (int w = 0; w < NW; ++w)
+			{
+				sv[w] = __funnelshift_r(r2l[w], (w + 1 < NW) ? r2l[w + 1 < NW ? w + 1 : 0] : 0u, r);
+				svn[w] = __funnelshift_r(n2r[w], (w + 1 < NW) ? n2r[w + 1 < NW ? w + 1 : 0] : 0u, r);
+			}
+#pragma unroll
+			for (int q = 0; q < NW; ++q)
+			{
+				int mml = 0;
+#pragma unroll
+				for (int k = 0; k < NW - q; ++k)
+				{
+					const int w = q + k;
+					mml += __popc((sv[w] ^ f1l[k]) & v1[k] & ~svn[w] & low_bits(FULL - 32 * w - r));
+				}
+				if (plain && mml <= (int)F.thr_env[32 * q + r])
+				{
+					if (nq < kLaneQCap) sts_u16(queue + 64u * (uint32_t)nq, (uint32_t)(32 * q + r));
+					++nq;
+				}
+			}
+		}
+	}
+	if (nq > kLaneQCap) plain = false;
+	uint32_t key = kNoKey;
+	for (int c = 0; c < kLaneQCap; ++c)
+	{
+		const bool mine = plain && c < nq;
+		if (!__any_sync(kFull, mine)) break;
+		if (mine)
+		{
+			const int o = (int)lds_u16(queue + 64u * (uint32_t)c);
+			int mm, tot;
+			lane_exact_mm_n<NW, FULL>(o, f1h, f1l, n1, r2h, r2l, n2r, mm, tot);
+			if (tot > 0 && tot - mm >= (int)T.mmin[tot]) key = min(key, lane_candidate_key_n<NW, FULL>(A, o, tot - mm, mm, f1h, f1l, n1, r2h, r2l, n2r));
+		}
+	}
+	int fwd = -1, rev = -1;
+	if (__any_sync(kFull, plain && key == kNoKey))
+	{
+		fwd = lane_adapter_scan_n<NW, FULL>(A, T, f1h, f1l, n1, A.a1h, A.a1l, A.a1n);
+		rev = lane_adapter_scan_n<NW, FULL>(A, T, f2h, f2l, n2, A.a2h, A.a2l, A.a2n);
+	}
+	lane_finish<FULL, NW>(A, p, plain, key, fwd, rev, n1, n2, scr);
+	return __ballot_sync(kFull, member && !plain);
+}
+
 // general path for one pair of the tile: the four rows are copied from global memory into the warp's buffer and handed to the
 // warp-cooperative code of spg_kernel.cuh
 template <int NW>
@@ -631,8 +974,12 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 	// Pairs that are not two full-length reads of A/C/G/T are collected and handed to the general path 32 at a time (its code is
 	// large and would otherwise be fetched anew for one pair in every tile)
 	auto flush_rare = [&]() {
-		for (int e = 0; e < n_rare; ++e)
+		uint32_t rest = n_rare >= 32 ? 0xFFFFFFFFu : ((1u << n_rare) - 1u);
+		if (n_rare > 0 && A.n_lanes) rest = lane_tile_n<NW, FULL>(A, T, F, rare, n_rare, queue, scr, lane); // pairs with N: one per lane
+		while (rest)
 		{
+			const int e = __ffs((int)rest) - 1;
+			rest &= rest - 1;
 			const uint2 ent = lds_v2(rare + 8u * (uint32_t)e);
 			lane_general_pair<NW>(A, T, wbase, ent.x, (int)(ent.y & 0xFFFFu), (int)(ent.y >> 16), lane);
 		}
@@ -783,53 +1130,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 		}
 
 		// ---- lengths, quality trimming, record ----
-		int n1 = FULL, n2 = FULL, best_offset = -1;
-		uint32_t flags = 0;
-		if (key != kNoKey) // insert hit (AnalysisWorker.cpp:269-302)
-		{
-			best_offset = (int)(key & 0xFFFFu);
-			n1 = n2 = FULL - best_offset;
-			flags |= SPG_F_INSERT;
-		}
-		else if (fwd >= 0 || rev >= 0) // adapter-only hit (:410-426)
-		{
-			flags |= SPG_F_ADAPTER;
-			if (fwd >= 0) n1 = fwd;
-			if (rev >= 0) n2 = rev;
-			if (fwd < 0) n1 = min(n1, rev);
-			if (rev < 0) n2 = min(n2, fwd);
-		}
-		if (A.qcut > 0) // :430-434
-		{
-			const size_t goff = (size_t)p * A.stride;
-			int t1 = -1, t2 = -1;
-			if (A.qwin == 5 && plain) // 16 qualities in registers, twelve window starts at a time from the 3' end
-			{
-				int e1 = n1, e2 = n2;
-				for (int k = 0; k < 8; ++k)
-				{
-					if (t1 < 0 && e1 >= 16) t1 = lane_trim_quality5(A, A.q1 + goff, e1);
-					if (t2 < 0 && e2 >= 16) t2 = lane_trim_quality5(A, A.q2 + goff, e2);
-					e1 -= 12;
-					e2 -= 12;
-					if (!((t1 < 0 && e1 >= 16) || (t2 < 0 && e2 >= 16))) break;
-				}
-			}
-			if (__any_sync(kFull, plain && t1 < 0)) t1 = lane_trim_quality(A, A.q1 + goff, n1, plain && t1 < 0, scr, t1);
-			if (__any_sync(kFull, plain && t2 < 0)) t2 = lane_trim_quality(A, A.q2 + goff, n2, plain && t2 < 0, scr, t2);
-			if (t1 < n1) flags |= SPG_F_Q1;
-			if (t2 < n2) flags |= SPG_F_Q2;
-			n1 = t1;
-			n2 = t2;
-		}
-		// (-ncut: a read without N is never cut)
-		if (plain)
-		{
-			uint2 rec;
-			rec.x = (uint32_t)n1 | ((uint32_t)n2 << 16);
-			rec.y = ((uint32_t)best_offset & 0xFFFFu) | (flags << 16);
-			*reinterpret_cast<uint2*>(A.out + p) = rec;
-		}
+		lane_finish<FULL>(A, p, plain, key, fwd, rev, nullptr, nullptr, scr);
 
 		// ---- everything else waits for the general path ----
 		const uint32_t rest = __ballot_sync(kFull, active && !plain);

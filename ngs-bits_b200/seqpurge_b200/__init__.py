@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("SPG_LIB") or os.path.join(os.path.dirname(_HERE), "li
 MAXLEN = 1000
 F_INSERT, F_ADAPTER, F_Q1, F_Q2, F_N1, F_N2 = 1, 2, 4, 8, 16, 32
 PAIR_OK, PAIR_BAD_BASE_R2, PAIR_TOO_LONG, PAIR_BAD_BASE_EC = 0, 1, 2, 3
-OPT_FORCE_BYTEWISE, OPT_GRID_CTAS_PER_SM, OPT_MIN_BLOCKS, OPT_TILE_PAIRS, OPT_STAGES, OPT_FULL_LEN, OPT_KERNEL, OPT_SEED_SCAN, OPT_ZERO_COPY_QUALS = 1, 2, 3, 4, 5, 6, 7, 8, 9
+OPT_FORCE_BYTEWISE, OPT_GRID_CTAS_PER_SM, OPT_MIN_BLOCKS, OPT_TILE_PAIRS, OPT_STAGES, OPT_FULL_LEN, OPT_KERNEL, OPT_SEED_SCAN, OPT_ZERO_COPY_QUALS, OPT_N_LANES = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 KERNEL_AUTO, KERNEL_WARP_PER_PAIR, KERNEL_LANE_PER_PAIR = 0, 1, 2
 
 RESULT_DTYPE = np.dtype([("len1", "<u2"), ("len2", "<u2"), ("best_offset", "<i2"), ("flags", "u1"), ("status", "u1")])

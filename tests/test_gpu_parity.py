@@ -371,6 +371,7 @@ def test_plane_width_boundaries(sp, L):
 @pytest.mark.parametrize("params", [
     dict(qwin=40, qcut=20), dict(qwin=1, qcut=30), dict(qwin=16, qcut=10), dict(qwin=17, qcut=25),
     dict(match_perc=50.0, mep=1e-3), dict(match_perc=100.0), dict(mep=1e-12), dict(ncut=1), dict(qcut=0, ncut=0), dict(qoff=64, qcut=5),
+    dict(mep=1.0, match_perc=0.0), dict(mep=2.0, match_perc=30.0),
 ], ids=lambda p: ",".join(f"{k}={v}" for k, v in p.items()))
 def test_parameter_corners(sp, params):
     """Window sizes on both sides of the fast paths (<= 8 paired, <= 32 scan, > 32 general), permissive and strict match filters
@@ -446,6 +447,10 @@ LANE_CASES = {
     "adapter_only_hits": (150, 150, dict(insert_mean=140, insert_sd=25, error_rate=0.12, n_rate=0.0, lowq_tail=2.0), dict()),
     "short_adapters_19": (100, 100, dict(insert_mean=90, insert_sd=25, error_rate=0.1, n_rate=0.0, a1="CTGTCTCTTATACACATCT", a2="CTGTCTCTTATACACATCT"),
                           dict(a1="CTGTCTCTTATACACATCT", a2="CTGTCTCTTATACACATCT")),
+    "many_n_runs": (150, 150, dict(insert_mean=140, insert_sd=60, error_rate=0.02, n_rate=0.004, n_runs=0.3, lowq_tail=5.0), dict(ncut=7)),
+    "single_n_cut": (126, 126, dict(insert_mean=120, insert_sd=60, error_rate=0.02, n_rate=0.003, n_runs=0.1), dict(ncut=1)),
+    "n_250_ncut3": (250, 250, dict(insert_mean=170, insert_sd=60, error_rate=0.03, n_rate=0.002, n_runs=0.2, lowq_tail=10.0), dict(ncut=3, qcut=20)),
+    "n_300_no_ncut": (300, 300, dict(insert_mean=250, insert_sd=120, error_rate=0.02, n_rate=0.002, n_runs=0.1), dict(ncut=0)),
     "n_and_ragged_mix": (151, 152, dict(insert_mean=160, insert_sd=90, error_rate=0.02, n_rate=0.002, n_runs=0.05, lowq_tail=10.0), dict()),
 }
 
