@@ -378,30 +378,42 @@ cudaError_t launch_nw(const spg::KArgs& a, int minb, int sm_count, int ctas_per_
 // The lane-per-pair kernel (spg_lanes.cuh) of one read length: 8 consumer warps + 1 producer warp, compiled for 2 resident CTAs per
 // SM. The ring is as deep as two resident CTAs allow (2..4 stages of 32 pairs' base rows).
 #ifndef SPG_LANE_CW
-#define SPG_LANE_CW 12
+#define SPG_LANE_CW 24
 #endif
 #ifndef SPG_LANE_MINB
-#define SPG_LANE_MINB 2
+#define SPG_LANE_MINB 1
 #endif
-constexpr int kLaneCW = SPG_LANE_CW, kLaneMinB = SPG_LANE_MINB;
+#ifndef SPG_LANE_CW_LONG
+#define SPG_LANE_CW_LONG 24 // reads of more than 160 bases (8 or 10 plane words per read: more registers per lane)
+#endif
+#ifndef SPG_LANE_MINB_LONG
+#define SPG_LANE_MINB_LONG 1
+#endif
+template <int NW>
+struct LaneCfg
+{
+	static constexpr int CW = NW <= 5 ? SPG_LANE_CW : SPG_LANE_CW_LONG;
+	static constexpr int MINB = NW <= 5 ? SPG_LANE_MINB : SPG_LANE_MINB_LONG;
+};
 template <int NW, int FULL>
 cudaError_t launch_lanes(spg::KArgs a, int sm_count, int ctas_per_sm, int stages_opt, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
 {
+	constexpr int CW = LaneCfg<NW>::CW, MINB = LaneCfg<NW>::MINB;
 	const size_t stage = spg::lane_stage_bytes(a.stride);
-	const size_t warps = (size_t)kLaneCW * spg::LaneSmem<NW>::kWarpBytes;
+	const size_t warps = (size_t)CW * spg::LaneSmem<NW>::kWarpBytes;
 	int stages = spg::kLaneStagesMax;
-	while (stages > 2 && kLaneMinB * (stages * stage + warps + 6 * 1024) > 227 * 1024) --stages;
+	while (stages > 2 && MINB * (stages * stage + warps + 6 * 1024) > 227 * 1024) --stages;
 	if (stages_opt >= 2 && stages_opt <= spg::kLaneStagesMax) stages = stages_opt;
 	a.stages = stages;
 	a.tile_pairs = 32;
 	const size_t smem = stages * stage + warps;
 	int occ = 1;
-	cudaError_t e = resident_ctas(spg::trim_lanes_kernel<NW, FULL, kLaneCW, kLaneMinB>, *occ_cache, (kLaneCW + 1) * 32, smem, mu, occ);
+	cudaError_t e = resident_ctas(spg::trim_lanes_kernel<NW, FULL, CW, MINB>, *occ_cache, (CW + 1) * 32, smem, mu, occ);
 	if (e != cudaSuccess) return e;
 	const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, occ) : occ;
 	const long long n_tiles = (a.n_pairs + 31) / 32;
 	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * per_sm);
-	spg::trim_lanes_kernel<NW, FULL, kLaneCW, kLaneMinB><<<grid, (kLaneCW + 1) * 32, smem, stream>>>(a);
+	spg::trim_lanes_kernel<NW, FULL, CW, MINB><<<grid, (CW + 1) * 32, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 
@@ -1043,7 +1055,7 @@ int spg_last_kernel(spg_ctx* ctx, char* name, int cap)
 	if (name && cap > 0)
 	{
 		if (v == 0) snprintf(name, (size_t)cap, "none");
-		else if (layout == 2) snprintf(name, (size_t)cap, "spg::trim_lanes_kernel<NW=%d,FULL=%d,CW=%d,MINB=%d>", nw, full, kLaneCW, kLaneMinB);
+		else if (layout == 2) snprintf(name, (size_t)cap, "spg::trim_lanes_kernel<NW=%d,FULL=%d,CW=%d,MINB=%d>", nw, full, nw <= 5 ? LaneCfg<5>::CW : LaneCfg<8>::CW, nw <= 5 ? LaneCfg<5>::MINB : LaneCfg<8>::MINB);
 		else snprintf(name, (size_t)cap, "spg::trim_kernel<NW=%d,CW=%d,MINB=%d,FULL=%d>", nw, kCW, ctx->min_blocks, layout == 1 ? full : 0);
 	}
 	return v;

@@ -313,9 +313,12 @@ __device__ __forceinline__ int lane_adapter_scan(const KArgs& A, const FullTab<N
 // base indicators (bit p = base p is A / C / G / T) are kept in shared memory (`ind`, [4][NW+1] words per lane, which of them an
 // adapter position needs comes from KArgs::a?off), shifted by the position inside the adapter and ANDed. Only the offsets that
 // survive (about 2 % of them) get the exact count of lane_adapter_scan, with the same multipliers and limits.
-template <int NW, int FULL>
-__device__ __forceinline__ int lane_adapter_scan_seeds(const KArgs& A, const FullTab<NW, FULL>& F, const uint32_t (&fh)[NW], const uint32_t (&fl)[NW], uint32_t ind,
-                                                       const uint16_t* aoff, uint32_t ah, uint32_t al, int maxmm)
+// HASN: the read may hold N (plane fn; N is packed like G): N positions match no adapter base, and every offset whose window holds
+// an N is a candidate as well (the pigeonhole argument only covers windows of A/C/G/T); candidates are then decided with the
+// general rule (pass table by number of compared bases), which equals the limit rule for windows without N.
+template <int NW, int FULL, bool HASN = false>
+__device__ __forceinline__ int lane_adapter_scan_seeds(const KArgs& A, const SmemTables& T, const FullTab<NW, FULL>& F, const uint32_t (&fh)[NW], const uint32_t (&fl)[NW],
+                                                       const uint32_t (&fn)[NW], uint32_t ind, const uint16_t* aoff, uint32_t ah, uint32_t al, uint32_t an, int maxmm)
 {
 	constexpr int QF = FullTab<NW, FULL>::QF;
 #pragma unroll
@@ -323,7 +326,7 @@ __device__ __forceinline__ int lane_adapter_scan_seeds(const KArgs& A, const Ful
 	{
 		sts_u32(ind + (0u * (NW + 1) + w) * 128u, ~(fh[w] | fl[w]) & low_mask_const(FULL - 32 * w)); // A = 00 (also what lies behind the read)
 		sts_u32(ind + (1u * (NW + 1) + w) * 128u, ~fh[w] & fl[w]);                                     // C = 01
-		sts_u32(ind + (2u * (NW + 1) + w) * 128u, fh[w] & fl[w]);                                      // G = 11
+		sts_u32(ind + (2u * (NW + 1) + w) * 128u, fh[w] & fl[w] & (HASN ? ~fn[w] : kFull));            // G = 11
 		sts_u32(ind + (3u * (NW + 1) + w) * 128u, fh[w] & ~fl[w]);                                     // T = 10
 	}
 #pragma unroll
@@ -331,6 +334,20 @@ __device__ __forceinline__ int lane_adapter_scan_seeds(const KArgs& A, const Ful
 	uint32_t cand[NW];
 #pragma unroll
 	for (int w = 0; w < NW; ++w) cand[w] = 0;
+	if (HASN) // offsets o with an N in [o, o+32): the N plane smeared towards lower positions
+	{
+#pragma unroll
+		for (int w = 0; w < NW; ++w) cand[w] = fn[w];
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1)
+		{
+			uint32_t sh[NW];
+#pragma unroll
+			for (int w = 0; w < NW; ++w) sh[w] = __funnelshift_r(cand[w], (w + 1 < NW) ? cand[w + 1 < NW ? w + 1 : 0] : 0u, d);
+#pragma unroll
+			for (int w = 0; w < NW; ++w) cand[w] |= sh[w];
+		}
+	}
 	const int nblk = A.a_size >> 2;
 #pragma unroll 1
 	for (int j = 0; j < nblk; ++j)
@@ -364,43 +381,90 @@ __device__ __forceinline__ int lane_adapter_scan_seeds(const KArgs& A, const Ful
 			const uint32_t sh = __funnelshift_r(fh[w], (w + 1 < NW) ? fh[w + 1 < NW ? w + 1 : 0] : 0u, b);
 			const uint32_t sl = __funnelshift_r(fl[w], (w + 1 < NW) ? fl[w + 1 < NW ? w + 1 : 0] : 0u, b);
 			const uint32_t x = (sh ^ ah) | (sl ^ al);
-			uint32_t mul = amul;
-			int lim = maxmm;
-			if constexpr (w >= QF)
+			if constexpr (HASN)
 			{
-				const int2 t = F.r1tail[w - QF][b];
-				mul = (uint32_t)t.x;
-				lim = t.y;
+				const int cnt = min(A.a_size, FULL - 32 * w - b);
+				const uint32_t sn = __funnelshift_r(fn[w], (w + 1 < NW) ? fn[w + 1 < NW ? w + 1 : 0] : 0u, b);
+				const uint32_t valid = low_bits(cnt) & ~an & ~sn;
+				if (cnt > 0 && ((T.passM[__popc(valid)] >> __popc(x & valid)) & 1u)) best = (uint32_t)(32 * w + b);
 			}
-			if (__popc(x * mul) <= lim) best = (uint32_t)(32 * w + b);
+			else
+			{
+				uint32_t mul = amul;
+				int lim = maxmm;
+				if constexpr (w >= QF)
+				{
+					const int2 t = F.r1tail[w - QF][b];
+					mul = (uint32_t)t.x;
+					lim = t.y;
+				}
+				if (__popc(x * mul) <= lim) best = (uint32_t)(32 * w + b);
+			}
 		}
 	});
 	return (int)best;
 }
 
 // ---- FastqEntry::trimQuality (src/cppNGS/FastqFileStream.cpp:52-87), one read per lane ----------------------------------------------------
-// Window 5 (the default), trimming point within the last 16 bases: the 16 quality bytes are taken from global memory into
-// registers (only the sectors that hold the end of the read are fetched), the twelve window sums slide down from the 3' end
-// (sign bits of sum - threshold collected by funnel shifts), "quality >= cutoff" of the 16 bases by one SWAR addition per word.
-// Works on the raw bytes (thresholds shifted by the quality offset), which is the reference's signed-char arithmetic as long as
-// all bytes are below 0x80. n: end of the 16 bases looked at (the read's length, or 12, 24, ... less: the search goes on to the left
-// when none of the twelve windows passes). Returns the new length, or -1: no passing window here (or fewer than 16 bases, a byte
-// >= 0x80 -- then the general search decides).
-__device__ __forceinline__ int lane_trim_quality5(const KArgs& A, const uint8_t* qrow, int n)
+// Window 5 (the default) in registers, on the raw bytes (thresholds shifted by the quality offset), which is the reference's
+// signed-char arithmetic as long as all bytes are below 0x80 (anything else: the general search).
+// (1) lane_last_good: the highest position below n whose quality reaches the cutoff, 16 aligned bytes per step from the 3' end. A
+//     window that starts above it holds only bases below the cutoff and cannot pass, so the search proper starts there -- long
+//     low-quality tails cost one load and a few SWAR instructions per 16 bases instead of one window sum per base.
+// (2) lane_quality5_block: 16 qualities [lo, lo+16), the window starts lo .. e-5 among them from the top: twelve sliding sums (sign
+//     bits of sum - threshold collected by funnel shifts), "quality >= cutoff" of the 16 bases by one SWAR addition per word.
+// Only the sectors that hold the end of the read are ever fetched (the quality planes may even live in pinned host memory).
+
+// bit j of the result: byte j of the 16 (v[j/4], byte j%4) is >= cutb (1..127); all bytes must be below 0x80
+__device__ __forceinline__ uint32_t lane_ge16(const uint32_t (&v)[4], int cutb)
 {
-	const int cutb = A.qcut + A.qoff, thrb = A.qthr + 5 * A.qoff;
-	if (n < 16 || cutb < 1 || cutb > 127) return -1;
-	// two aligned 16-byte loads cover the 16 bytes wherever they start (one request per half sector: the quality planes may live in
-	// pinned host memory, where every load instruction is a read over PCIe); the second one is not needed for an aligned start
-	const uintptr_t a = (uintptr_t)qrow + (uintptr_t)(n - 16);
+	// byte + 128 - cutb carries into bit 7; the four bits 7 of a word are gathered into the top nibble by a multiplication
+	uint32_t ge = 0;
+#pragma unroll
+	for (int k = 3; k >= 0; --k) ge = __funnelshift_l(((v[k] + (uint32_t)(0x80 - cutb) * 0x01010101u) & 0x80808080u) * 0x00204081u, ge, 4);
+	return ge;
+}
+
+// highest position p < n with quality >= cutoff; -1: none; -2: a byte >= 0x80 was met
+__device__ __forceinline__ int lane_last_good(const uint8_t* qrow, int n, int cutb)
+{
+	int end = n;
+	while (end > 0)
+	{
+		const uintptr_t a = ((uintptr_t)qrow + (uintptr_t)(end - 1)) & ~(uintptr_t)15; // aligned chunk that holds position end-1
+		const int p0 = (int)((intptr_t)a - (intptr_t)(uintptr_t)qrow);                    // position of its first byte (may lie in front of the row)
+		const uint4 c = __ldg(reinterpret_cast<const uint4*>(a));
+		const uint32_t v[4] = {c.x, c.y, c.z, c.w};
+		const uint32_t in = low_bits(end - p0) & ~low_bits(-p0); // bytes of the chunk that are positions [max(p0,0), end)
+		// a byte >= 0x80 inside the read: the general search decides (bit 7 of byte j -> bit j by the same multiplication)
+		uint32_t hb = 0;
+#pragma unroll
+		for (int k = 3; k >= 0; --k) hb = __funnelshift_l((v[k] & 0x80808080u) * 0x00204081u, hb, 4);
+		if (hb & in) return -2;
+		uint32_t w[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) w[k] = v[k] & 0x7F7F7F7Fu; // bytes outside the read may be anything
+		const uint32_t ge = lane_ge16(w, cutb) & in;
+		if (ge) return p0 + 31 - __clz(ge);
+		end = p0;
+	}
+	return -1;
+}
+
+// windows of 5 starting at lo .. e-5 (lo <= e-5 is not required), bytes [lo, lo+16) of the row. Returns the new length if one of them
+// passes (highest start first, then the trailing bases below the cutoff are dropped), -1 if none does, -2 for a byte >= 0x80.
+__device__ __forceinline__ int lane_quality5_block(const uint8_t* qrow, int lo, int e, int cutb, int thrb)
+{
+	// two aligned 16-byte loads cover the 16 bytes wherever they start; the second one is not needed for an aligned start
+	const uintptr_t a = (uintptr_t)qrow + (uintptr_t)lo;
 	const uint32_t off = (uint32_t)(a & 15u);
 	const uint4* wp = reinterpret_cast<const uint4*>(a - off);
-	const uint4 lo = __ldg(wp);
-	uint4 hi = make_uint4(0u, 0u, 0u, 0u);
-	if (off) hi = __ldg(wp + 1);
+	const uint4 c0 = __ldg(wp);
+	uint4 c1 = make_uint4(0u, 0u, 0u, 0u);
+	if (off) c1 = __ldg(wp + 1);
 	// words off/4 .. off/4+4 of the eight, then the byte shift inside a word
 	const bool s2 = off & 8u, s1 = off & 4u;
-	const uint32_t x0 = s2 ? lo.z : lo.x, x1 = s2 ? lo.w : lo.y, x2 = s2 ? hi.x : lo.z, x3 = s2 ? hi.y : lo.w, x4 = s2 ? hi.z : hi.x, x5 = s2 ? hi.w : hi.y;
+	const uint32_t x0 = s2 ? c0.z : c0.x, x1 = s2 ? c0.w : c0.y, x2 = s2 ? c1.x : c0.z, x3 = s2 ? c1.y : c0.w, x4 = s2 ? c1.z : c1.x, x5 = s2 ? c1.w : c1.y;
 	uint32_t w[5];
 	w[0] = s1 ? x1 : x0;
 	w[1] = s1 ? x2 : x1;
@@ -410,13 +474,9 @@ __device__ __forceinline__ int lane_trim_quality5(const KArgs& A, const uint8_t*
 	const uint32_t boff = off & 3u;
 	uint32_t v[4];
 #pragma unroll
-	for (int k = 0; k < 4; ++k) v[k] = __funnelshift_r(w[k], w[k + 1], 8u * boff); // bytes of positions n-16+4k ..
-	if ((v[0] | v[1] | v[2] | v[3]) & 0x80808080u) return -1;
-	// bit j: quality of position n-16+j reaches the cutoff (byte + 128 - cutb carries into bit 7; the four bits 7 are gathered
-	// into the top nibble by a multiplication)
-	uint32_t ge = 0;
-#pragma unroll
-	for (int k = 3; k >= 0; --k) ge = __funnelshift_l(((v[k] + (uint32_t)(0x80 - cutb) * 0x01010101u) & 0x80808080u) * 0x00204081u, ge, 4);
+	for (int k = 0; k < 4; ++k) v[k] = __funnelshift_r(w[k], w[k + 1], 8u * boff); // bytes of positions lo+4k ..
+	if ((v[0] | v[1] | v[2] | v[3]) & 0x80808080u) return -2;
+	const uint32_t ge = lane_ge16(v, cutb); // bit j: quality of position lo+j reaches the cutoff
 	auto byte_at = [&](int j) -> int { return (int)prmt(v[j >> 2], 0u, 0x4440u | (uint32_t)(j & 3)); };
 	int b[16];
 #pragma unroll
@@ -427,14 +487,42 @@ __device__ __forceinline__ int lane_trim_quality5(const KArgs& A, const uint8_t*
 	for (int j = 10; j >= 0; --j)
 	{
 		sd += b[j] - b[j + 5];
-		fail = __funnelshift_l((uint32_t)sd, fail, 1); // bit (10 - j + ...) : the sign of the newest window enters at bit 0
+		fail = __funnelshift_l((uint32_t)sd, fail, 1); // the sign of the newest window enters at bit 0: in the end bit j = window start lo+j
 	}
-	// fail bit i belongs to window start j = i (j = 11 entered first and was shifted up eleven times ... bit 11; j = 0 is bit 0)
-	const uint32_t pass = ~fail & 0xFFFu;
+	const uint32_t pass = ~fail & low_bits(min(e - lo - 4, 12)); // window starts lo .. e-5
 	if (pass == 0) return -1;
-	const int t = 31 - __clz(pass);                 // highest passing window start (relative to n-16)
-	const uint32_t keep = ge & low_bits(t + 5);     // bases below the window's end that reach the cutoff (not empty: the window's mean does)
-	return n - 16 + 32 - __clz(keep);               // one past the last of them: trailing bases below the cutoff are dropped
+	const int t = 31 - __clz(pass);             // highest passing window start (relative to lo)
+	const uint32_t keep = ge & low_bits(t + 5); // bases below the window's end that reach the cutoff (not empty: the window's mean does)
+	return lo + 32 - __clz(keep);               // one past the last of them: trailing bases below the cutoff are dropped
+}
+
+// the whole search for one read; -2: the general search has to decide (a byte >= 0x80, thresholds outside 1..127)
+__device__ __forceinline__ int lane_trim_quality5(const KArgs& A, const uint8_t* qrow, int n)
+{
+	const int cutb = A.qcut + A.qoff, thrb = A.qthr + 5 * A.qoff;
+	if (cutb < 1 || cutb > 127) return -2;
+	if (n < 5) return n; // shorter than the window: not trimmed
+	// the twelve windows at the 3' end first (most reads end there); only then the jump over a long low-quality tail
+	int e = n;
+	{
+		const int lo = max(e - 16, 0);
+		const int r = lane_quality5_block(qrow, lo, e, cutb, thrb);
+		if (r != -1) return r;
+		if (lo == 0) return 0; // every window failed: the read is emptied
+		e = lo + 4;            // what is left: the window starts 0 .. lo-1
+	}
+	const int g = lane_last_good(qrow, e, cutb);
+	if (g == -2) return -2;
+	if (g < 0) return 0;  // no base reaches the cutoff, so no window does
+	e = min(e, g + 5);    // windows that start above g hold only bases below the cutoff
+	for (;;)
+	{
+		const int lo = max(e - 16, 0);
+		const int r = lane_quality5_block(qrow, lo, e, cutb, thrb);
+		if (r != -1) return r;
+		if (lo == 0) return 0;
+		e = lo + 4;
+	}
 }
 
 // General search: any window <= 8, any trimming point.
@@ -564,18 +652,11 @@ __device__ __forceinline__ void lane_finish(const KArgs& A, uint32_t p, bool pla
 	if (A.qcut > 0) // :430-434
 	{
 		const size_t goff = (size_t)p * A.stride;
-		int t1 = -1, t2 = -1;
-		if (A.qwin == 5 && plain) // 16 qualities in registers, twelve window starts at a time from the 3' end
+		int t1 = -2, t2 = -2; // -2: not decided yet
+		if (A.qwin == 5 && plain)
 		{
-			int e1 = n1, e2 = n2;
-			for (int k = 0; k < 8; ++k)
-			{
-				if (t1 < 0 && e1 >= 16) t1 = lane_trim_quality5(A, A.q1 + goff, e1);
-				if (t2 < 0 && e2 >= 16) t2 = lane_trim_quality5(A, A.q2 + goff, e2);
-				e1 -= 12;
-				e2 -= 12;
-				if (!((t1 < 0 && e1 >= 16) || (t2 < 0 && e2 >= 16))) break;
-			}
+			t1 = lane_trim_quality5(A, A.q1 + goff, n1);
+			t2 = lane_trim_quality5(A, A.q2 + goff, n2);
 		}
 		if (__any_sync(kFull, plain && t1 < 0)) t1 = lane_trim_quality(A, A.q1 + goff, n1, plain && t1 < 0, scr, t1);
 		if (__any_sync(kFull, plain && t2 < 0)) t2 = lane_trim_quality(A, A.q2 + goff, n2, plain && t2 < 0, scr, t2);
@@ -756,6 +837,7 @@ __device__ __forceinline__ int lane_adapter_scan_n(const KArgs& A, const SmemTab
 // needs the general path.
 template <int NW, int FULL>
 __device__ __noinline__ uint32_t lane_tile_n(const KArgs& A, const SmemTables& T, const FullTab<NW, FULL>& F, uint32_t list, int n_entries, uint32_t queue, uint32_t scr, int lane)
+// (scr: this lane's word 0 of the warp's copy area: indicator planes of the seed scans, window of the general quality search)
 {
 	uint32_t p = 0;
 	bool plain = false;
@@ -806,11 +888,12 @@ __device__ __noinline__ uint32_t lane_tile_n(const KArgs& A, const SmemTables& T
 			for (int q = 0; q < NW; ++q)
 			{
 				int mml = 0;
+				const int kmax = min(NW - q, sweep_words(FULL - 32 * q)); // folded after unrolling; see sweep_words
 #pragma unroll
 				for (int k = 0; k < NW - q; ++k)
 				{
 					const int w = q + k;
-					mml += __popc((sv[w] ^ f1l[k]) & v1[k] & ~svn[w] & low_bits(FULL - 32 * w - r));
+					if (k < kmax) mml += __popc((sv[w] ^ f1l[k]) & v1[k] & ~svn[w] & low_bits(FULL - 32 * w - r));
 				}
 				if (plain && mml <= (int)F.thr_env[32 * q + r])
 				{
@@ -837,8 +920,16 @@ __device__ __noinline__ uint32_t lane_tile_n(const KArgs& A, const SmemTables& T
 	int fwd = -1, rev = -1;
 	if (__any_sync(kFull, plain && key == kNoKey))
 	{
-		fwd = lane_adapter_scan_n<NW, FULL>(A, T, f1h, f1l, n1, A.a1h, A.a1l, A.a1n);
-		rev = lane_adapter_scan_n<NW, FULL>(A, T, f2h, f2l, n2, A.a2h, A.a2l, A.a2n);
+		if (A.seed_ok)
+		{
+			fwd = lane_adapter_scan_seeds<NW, FULL, true>(A, T, F, f1h, f1l, n1, scr, A.a1off, A.a1h, A.a1l, A.a1n, A.a1maxmm);
+			rev = lane_adapter_scan_seeds<NW, FULL, true>(A, T, F, f2h, f2l, n2, scr, A.a2off, A.a2h, A.a2l, A.a2n, A.a2maxmm);
+		}
+		else
+		{
+			fwd = lane_adapter_scan_n<NW, FULL>(A, T, f1h, f1l, n1, A.a1h, A.a1l, A.a1n);
+			rev = lane_adapter_scan_n<NW, FULL>(A, T, f2h, f2l, n2, A.a2h, A.a2l, A.a2n);
+		}
 	}
 	lane_finish<FULL, NW>(A, p, plain, key, fwd, rev, n1, n2, scr);
 	return __ballot_sync(kFull, member && !plain);
@@ -1119,8 +1210,8 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 		{
 			if (A.seed_ok)
 			{
-				fwd = lane_adapter_scan_seeds<NW, FULL>(A, F, f1h, f1l, copy, A.a1off, A.a1h, A.a1l, A.a1maxmm);
-				rev = lane_adapter_scan_seeds<NW, FULL>(A, F, f2h, f2l, copy, A.a2off, A.a2h, A.a2l, A.a2maxmm);
+				fwd = lane_adapter_scan_seeds<NW, FULL>(A, T, F, f1h, f1l, f1h, copy, A.a1off, A.a1h, A.a1l, A.a1n, A.a1maxmm);
+				rev = lane_adapter_scan_seeds<NW, FULL>(A, T, F, f2h, f2l, f2h, copy, A.a2off, A.a2h, A.a2l, A.a2n, A.a2maxmm);
 			}
 			else
 			{

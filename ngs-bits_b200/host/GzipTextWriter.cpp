@@ -231,7 +231,12 @@ void GzipTextWriter::writerLoop()
 				p = std::move(queue_.front());
 				queue_.pop_front();
 			}
-			if (bgzf_ && !pool_) compressPieceBgzf(p.get()); // serial BGZF: deflate here, in order
+			if (bgzf_ && !pool_) // serial BGZF: deflate here, in order
+			{
+				compressPieceBgzf(p.get());
+				std::unique_lock<std::mutex> l(mu_);
+				if (failure_) break; // the piece's buffer is not valid output: nothing of it is written
+			}
 			if (gz)
 			{
 				size_t off = 0; // gzwrite takes an unsigned length

@@ -15,6 +15,7 @@
 namespace seqpurge
 {
 
+
 // name -> value strings as a qcML file holds them (integers as such, doubles with two decimals)
 std::vector<std::pair<std::string, std::string>> qcMetrics(const spg_qc_stats& s);
 

@@ -6,6 +6,33 @@
 namespace seqpurge
 {
 
+// QCValue::toString -> QString::number(v, 'f', 2). Qt formats through the double-conversion library, whose fixed notation resolves
+// an exact tie upwards (like ECMAScript's toFixed: 0.125 -> "0.13"), where printf resolves it to even ("0.12"). The reference's golden
+// ReadQC_out4.qcML holds such a value (125 000 bases = 0.125 MB), so the third decimal of the exact expansion decides here.
+std::string fixed2(double v)
+{
+	if (v != v) return "nan"; // QString::number prints "nan" (glibc would print "-nan" for 0/0)
+	if (!(v >= 0.0) || v > 1e15) // negative or huge: not produced by these statistics
+	{
+		char b[64];
+		snprintf(b, sizeof(b), "%.2f", v);
+		return b;
+	}
+	char buf[128];
+	snprintf(buf, sizeof(buf), "%.40f", v); // glibc prints the exact binary value; 40 decimals are far beyond the third one
+	std::string s(buf);
+	const size_t dot = s.find('.');
+	const bool up = s[dot + 3] >= '5';
+	long long cents = 0; // integer part and two decimals as one number
+	for (size_t i = 0; i < dot + 3; ++i)
+		if (s[i] != '.') cents = cents * 10 + (s[i] - '0');
+	if (up) ++cents;
+	char out[64];
+	snprintf(out, sizeof(out), "%lld.%02lld", cents / 100, cents % 100);
+	return out;
+}
+
+
 void BaseCounts::inc(char base)
 {
 	switch (base)
@@ -24,12 +51,6 @@ long long BaseCounts::max() const { return std::max(std::max(a, c), std::max(g, 
 
 namespace
 {
-std::string fixed2(double v)
-{
-	char buf[64];
-	snprintf(buf, sizeof(buf), "%.2f", v);
-	return buf;
-}
 std::string right4(long long v)
 {
 	char buf[32];

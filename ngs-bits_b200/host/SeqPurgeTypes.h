@@ -17,6 +17,9 @@
 namespace seqpurge
 {
 
+// QString::number(v, 'f', 2) as the reference prints percentages and qcML values: two decimals, an exact tie goes up, NaN is "nan"
+std::string fixed2(double v);
+
 const int MAXLEN = 1000; // src/SeqPurge/Auxilary.h:12
 
 // exception kinds of cppCORE (src/cppCORE/Exceptions.h:15-174); the tool prints the message and exits with 1

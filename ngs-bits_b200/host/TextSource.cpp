@@ -72,7 +72,13 @@ long bgzfBlockSize(const uint8_t* p, size_t n)
 	while (off + 4 <= 12 + xlen)
 	{
 		const size_t slen = (size_t)p[off + 2] | ((size_t)p[off + 3] << 8);
-		if (p[off] == 'B' && p[off + 1] == 'C' && slen == 2 && off + 6 <= 12 + xlen) return (long)((size_t)p[off + 4] | ((size_t)p[off + 5] << 8)) + 1;
+		if (p[off] == 'B' && p[off + 1] == 'C' && slen == 2 && off + 6 <= 12 + xlen)
+		{
+			const size_t bs = ((size_t)p[off + 4] | ((size_t)p[off + 5] << 8)) + 1;
+			// a block holds at least its header, the extra field and the 8-byte trailer (CRC32, ISIZE): anything smaller is corrupt and would
+			// make the trailer reads of inflateJob point in front of the block
+			return bs >= 12 + xlen + 8 ? (long)bs : 0;
+		}
 		off += 4 + slen;
 	}
 	return 0;
@@ -159,8 +165,11 @@ private:
 			size_t total = 0;
 			for (const auto& b : j->blocks)
 			{
+				if (b.second < 12 + 8) throw Exception("corrupt BGZF block");
 				const uint8_t* e = j->comp.data() + b.first + b.second;
-				total += (size_t)e[-4] | ((size_t)e[-3] << 8) | ((size_t)e[-2] << 16) | ((size_t)e[-1] << 24);
+				const size_t isize = (size_t)e[-4] | ((size_t)e[-3] << 8) | ((size_t)e[-2] << 16) | ((size_t)e[-1] << 24);
+				if (isize > 65536) throw Exception("corrupt BGZF block"); // the format limits a block to 64 KiB of text
+				total += isize;
 			}
 			j->text.resize(total);
 			z_stream zs;

@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """Text summary of one `ncu --set full` capture of the trimming kernel: key raw metrics (per launch), stall reasons,
-pipe utilisation. usage: ncu_summary.py <file.ncu-rep> <pairs per launch>"""
+pipe utilisation. usage: ncu_summary.py <file.ncu-rep | raw-page .csv> <pairs per launch> [algorithmic bytes per pair] [--traffic out.json capture-name]"""
 import csv
 import subprocess
 import sys
 
 rep, pairs = sys.argv[1], float(sys.argv[2])
-out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+balg = float(sys.argv[3]) if len(sys.argv) > 3 and not sys.argv[3].startswith("--") else 608.0
 rows = list(csv.reader(out.splitlines()))
 hdr, unit, val = rows[0], rows[1], rows[-1]
 m = {h: (v, u) for h, u, v in zip(hdr, unit, val)}
@@ -25,7 +26,7 @@ rd, wr = f("dram__bytes_read.sum"), f("dram__bytes_write.sum")
 ru, wu = g("dram__bytes_read.sum")[1], g("dram__bytes_write.sum")[1]
 scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 rb, wb = rd * scale.get(ru, 1), wr * scale.get(wu, 1)
-print(f"dram traffic      : read {rb/1e6:.1f} MB + write {wb/1e6:.1f} MB per launch = {(rb+wb)/pairs:.1f} B per pair (algorithmic 608 B at 2x150)")
+print(f"dram traffic      : read {rb/1e6:.1f} MB + write {wb/1e6:.1f} MB per launch = {(rb+wb)/pairs:.1f} B per pair (algorithmic {balg:.0f} B)")
 print(f"dram throughput   : {g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')[0]} % of peak")
 inst = f("smsp__inst_executed.sum")
 print(f"warp instructions : {inst:.4g} per launch = {inst/pairs:.0f} per pair")
@@ -35,3 +36,11 @@ for p in ("alu", "fma", "xu", "lsu", "adu", "cbu", "uniform"):
 print("stall reasons (warps per issue-active cycle):")
 for s in ("wait", "not_selected", "long_scoreboard", "short_scoreboard", "math_pipe_throttle", "no_instruction", "branch_resolving", "barrier", "mio_throttle", "lg_throttle", "dispatch_stall", "sleeping", "membar"):
     print(f"  {s:20s} {g(f'smsp__average_warps_issue_stalled_{s}_per_issue_active.ratio')[0]}")
+
+if "--traffic" in sys.argv:
+    import json
+    i = sys.argv.index("--traffic")
+    commit = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    json.dump({"dram_bytes_per_pair": (rb + wb) / pairs, "kernel": g("Kernel Name")[0], "capture": sys.argv[i + 2], "commit": commit,
+               "pairs_per_launch": pairs, "how": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of bench.py's headline config"},
+              open(sys.argv[i + 1], "w"), indent=1)
