@@ -519,6 +519,14 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 			if (kmax >= std::min(tot / 4, ctx->a_size / 4)) seed = false;
 		}
 		a.seed_ok = (seed && ctx->seed_scan) ? 1 : 0;
+		{
+			// a full window (a_size bases) with one N compares a_size-1 bases; the N spoils at most one block
+			int kmax = -1;
+			const int tot = ctx->a_size - 1;
+			for (int mm = 0; mm <= tot; ++mm)
+				if ((ctx->tables.passA[tot] >> (tot - mm)) & 1u) kmax = mm;
+			a.seed_n1_ok = (a.seed_ok && kmax < ctx->a_size / 4 - 1) ? 1 : 0;
+		}
 		const int nwi = nw_for_stride(stride);
 		auto code = [](char c) { return c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0; };
 		for (int i = 0; i < 20; ++i)

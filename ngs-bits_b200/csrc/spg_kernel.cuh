@@ -77,6 +77,7 @@ struct KArgs
 	int full_ok;             // adapters without N in their first a_size bases and every pass set of steps 2/3 an interval 0..k of mismatches
 	int quals_on_host;       // lane kernel: q1 / q2 point into mapped pinned host memory (zero copy): no speculative prefetches over PCIe
 	int n_lanes;             // lane kernel: pairs with N take the N-aware lane path (0: the general path, SPG_OPT_N_LANES)
+	int seed_n1_ok;          // lane kernel: the same for a full window that holds one N (a_size-1 compared bases, one block lost)
 	int seed_ok;             // lane kernel: every passing window of steps 2/3 has fewer mismatches than complete 4-base adapter blocks (and full_ok)
 	uint16_t a1off[20];      // lane kernel: byte offset of the base-indicator plane (A,C,G,T -> 0..3 times (NW+1)*128) of adapter position i
 	uint16_t a2off[20];

@@ -334,10 +334,16 @@ __device__ __forceinline__ int lane_adapter_scan_seeds(const KArgs& A, const Sme
 	uint32_t cand[NW];
 #pragma unroll
 	for (int w = 0; w < NW; ++w) cand[w] = 0;
-	if (HASN) // offsets o with an N in [o, o+32): the N plane smeared towards lower positions
+	if (HASN)
 	{
+		// offsets o with an N in [o, o+32): the N plane smeared towards lower positions
+		int n_count = 0;
 #pragma unroll
-		for (int w = 0; w < NW; ++w) cand[w] = fn[w];
+		for (int w = 0; w < NW; ++w)
+		{
+			cand[w] = fn[w];
+			n_count += __popc(fn[w]);
+		}
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1)
 		{
@@ -346,6 +352,15 @@ __device__ __forceinline__ int lane_adapter_scan_seeds(const KArgs& A, const Sme
 			for (int w = 0; w < NW; ++w) sh[w] = __funnelshift_r(cand[w], (w + 1 < NW) ? cand[w + 1 < NW ? w + 1 : 0] : 0u, d);
 #pragma unroll
 			for (int w = 0; w < NW; ++w) cand[w] |= sh[w];
+		}
+		// A full window with ONE N still has a clean exact block when the parameters say so (KArgs::seed_n1_ok: fewer mismatches
+		// allowed on a_size-1 bases than blocks that the N leaves intact): then only the windows cut by the read's end need the
+		// explicit check. Reads with several N keep every window that holds one.
+		if (n_count == 1 && A.seed_n1_ok)
+		{
+			const int first_cut = FULL - A.a_size + 1; // first offset whose window is cut
+#pragma unroll
+			for (int w = 0; w < NW; ++w) cand[w] &= ~low_bits(first_cut - 32 * w);
 		}
 	}
 	const int nblk = A.a_size >> 2;
