@@ -64,7 +64,8 @@ typedef struct spg_params
 	int32_t ec;          /* -ec: error-correct insert-hit pairs; edited rows are returned in the slot */
 	int32_t qc;          /* -qc: also accumulate the raw-read statistics of every submitted batch (spg_qc_stats_get). 2: with the checks of
 	                        FastqEntry::validate as ReadQC runs them (src/cppNGS/FastqFileStream.cpp:3-48): bases of exactly A,C,G,T,N and
-	                        qualities of '!'..'J' (33..74), anything else counts in spg_qc_stats.errors */
+	                        qualities of '!'..'J' (33..74), anything else counts in spg_qc_stats.errors. +4 (i.e. 5 or 6): also fill the histograms behind
+	                        the three qcML plots (base_qualities, read_qualities, qscore_dist_*), which cost one shared-memory atomic per 32 bases */
 } spg_params;
 
 /* Per-pair output: everything OutputWorker / FastqWriter / TrimmingStatistics need (OutputWorker.cpp:36-77). 8 bytes. */
@@ -116,6 +117,11 @@ typedef struct spg_qc_stats
 	int64_t pileup[SPG_MAXLEN][5];        /* pileups_[cycle]: A, C, G, T, N (lower case counted like Pileup::inc) */
 	int64_t qsum_forward[SPG_MAXLEN];     /* qualities1_[cycle] before the division by the depth */
 	int64_t qsum_reverse[SPG_MAXLEN];     /* qualities2_[cycle] */
+	/* the accumulators behind the three qcML plots (StatisticsReads.cpp:60-61,74-77; plotted in getResult, :300-440) */
+	int64_t base_qualities[100];          /* base_qualities_[q]: bases by quality */
+	int64_t read_qualities[100];          /* read_qualities_[round(mean quality of the read)] (reads of length 0 do not count) */
+	int64_t qscore_dist_forward[60];      /* qscore_dist_r1 = Histogram(0, 60, 1) of the mean read quality, forward reads */
+	int64_t qscore_dist_reverse[60];      /* qscore_dist_r2, reverse reads */
 } spg_qc_stats;
 
 typedef struct spg_ctx spg_ctx;
@@ -209,6 +215,21 @@ typedef struct spg_fq_input
 #define SPG_FQ_BAD_HEADER 4      /* validate: "First header line does not start with '@'" (FastqFileStream.cpp:7-10) */
 #define SPG_FQ_BAD_HEADER2 5     /* validate: "Second header line does not start with '+'" (FastqFileStream.cpp:11-14) */
 
+/* Summary counters of one chunk, what OutputWorker::run adds to TrimmingStatistics (src/SeqPurge/OutputWorker.cpp:59-77), reduced on the
+   device from the result records. bases_perc_trim_sum of the reference is sum over reads of (o - len) / o in double, in job order; here
+   the exact integer sums per original length o are returned and the caller adds trimmed_bases_by_length[o] / o -- the same value up to the
+   rounding order of a floating-point sum (the reference's own order depends on which job finishes first). */
+typedef struct spg_fq_stats
+{
+	int64_t reads_trimmed_insert;  /* 2 per pair with an insert match */
+	int64_t reads_trimmed_adapter; /* 2 per pair with an adapter-only hit */
+	int64_t reads_trimmed_q;       /* reads that lost bases to trimQuality */
+	int64_t reads_trimmed_n;       /* reads that lost bases to trimN */
+	int64_t reads_removed;         /* reads not written (shorter than min_len, or mate removed without -out3) */
+	int64_t bases_remaining[SPG_MAXLEN];         /* [len]: reads of that length after trimming */
+	int64_t trimmed_bases_by_length[SPG_MAXLEN]; /* [o]: bases removed from reads of original length o */
+} spg_fq_stats;
+
 typedef struct spg_fq_output
 {
 	int32_t n_pairs;             /* pairs processed = min(records1, records2, max_pairs) */
@@ -223,6 +244,7 @@ typedef struct spg_fq_output
 	int32_t error_pair;          /* first pair with frame_status != 0 or results[].status != 0, or -1 */
 	int32_t max_len;             /* longest bases/qualities line of the chunk */
 	int32_t invalid_chars;       /* stats_only: != 0 if the chunk holds a base or quality that counts in spg_qc_stats.errors */
+	const spg_fq_stats* stats;   /* summary counters of this chunk (NULL with stats_only / fixed_trim) */
 } spg_fq_output;
 
 /* Attaches a FASTQ stream to a context (which provides parameters, tables, devices; it may have been created with n_slots = 0). */

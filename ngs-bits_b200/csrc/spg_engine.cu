@@ -640,7 +640,8 @@ int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, con
 	spg::QcArgs a;
 	a.bad_flag = bad_flag;
 	a.forward_only = forward_only ? 1 : 0;
-	a.strict = ctx->params.qc == 2 ? 1 : 0;
+	a.strict = (ctx->params.qc & 3) == 2 ? 1 : 0;
+	a.plots = (ctx->params.qc & 4) ? 1 : 0;
 	a.n_dev = n_dev;
 	a.b1 = b1;
 	a.q1 = q1;
@@ -651,6 +652,16 @@ int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, con
 	a.n_pairs = n;
 	a.stride = stride;
 	a.acc = d.d_qc;
+	// Histogram(0, 60, 1)::binIndex of an integral mean quality k, evaluated in double exactly as the reference does
+	// (floor((k - 0) / (60 - 0) * 60), src/cppCORE/Histogram.cpp:124): k / 60 * 60 may fall just below k
+	for (int k = 0; k < 100; ++k)
+	{
+		const double hmin = 0.0, hmax = 60.0;
+		volatile double x = ((double)k - hmin) / (hmax - hmin);
+		volatile double y = x * 60;
+		long b = (long)std::floor(y);
+		a.bin_of_int[k] = (uint8_t)std::min(59L, std::max(0L, b));
+	}
 	cudaError_t e = cudaSuccess;
 	switch (nw_for_stride(stride))
 	{
@@ -947,6 +958,16 @@ int spg_qc_stats_get(spg_ctx* ctx, spg_qc_stats* out)
 			for (int k = 0; k < 5; ++k) out->pileup[i][k] += (int64_t)tmp[(size_t)spg::kQcPile + 5 * i + k];
 			out->qsum_forward[i] += (int64_t)tmp[(size_t)spg::kQcQf + i];
 			out->qsum_reverse[i] += (int64_t)tmp[(size_t)spg::kQcQr + i];
+		}
+		for (int i = 0; i < 100; ++i)
+		{
+			out->base_qualities[i] += (int64_t)tmp[(size_t)spg::kQcBaseQual + i];
+			out->read_qualities[i] += (int64_t)tmp[(size_t)spg::kQcReadQual + i];
+		}
+		for (int i = 0; i < 60; ++i)
+		{
+			out->qscore_dist_forward[i] += (int64_t)tmp[(size_t)spg::kQcDistF + i];
+			out->qscore_dist_reverse[i] += (int64_t)tmp[(size_t)spg::kQcDistR + i];
 		}
 	}
 	return SPG_OK;

@@ -74,6 +74,7 @@ struct FqArgs
 	uint16_t* len[2];
 	int stride;
 	FqRec* rec[2];
+	unsigned long long* stats; // spg_fq_stats of this chunk as 64-bit words (5 counters, then the two histograms), or null
 	uint8_t* fstat;   // [max_pairs]
 	// output
 	const spg_result* res;
@@ -504,6 +505,39 @@ __global__ void __launch_bounds__(kFqOutPairs) fq_out_sizes(const __grid_constan
 	if (p < n) fq_pair_sizes(A, p, sz, l1, l2);
 	fq_block_scan4(sz, tot);
 	if (threadIdx.x < 4) A.out_block[threadIdx.x][blockIdx.x] = tot[threadIdx.x];
+	// summary counters (OutputWorker.cpp:59-77): per-CTA histograms in shared memory, one atomic per touched bin into the chunk's totals
+	if (A.stats != nullptr)
+	{
+		__shared__ uint32_t h_rem[SPG_MAXLEN], h_trim[SPG_MAXLEN], cnt[5];
+		for (int i = threadIdx.x; i < SPG_MAXLEN; i += kFqOutPairs) h_rem[i] = h_trim[i] = 0;
+		if (threadIdx.x < 5) cnt[threadIdx.x] = 0;
+		__syncthreads();
+		if (p < n)
+		{
+			const spg_result r = A.res[p];
+			const int o1 = A.len[0][p], o2 = A.len[1][p];
+			const bool ok1 = l1 >= A.min_len, ok2 = l2 >= A.min_len;
+			const uint32_t removed = (ok1 && ok2) ? 0u : ((A.singles && (ok1 || ok2)) ? 1u : 2u);
+			const uint32_t tq = ((r.flags & SPG_F_Q1) ? 1u : 0u) + ((r.flags & SPG_F_Q2) ? 1u : 0u);
+			const uint32_t tn = ((r.flags & SPG_F_N1) ? 1u : 0u) + ((r.flags & SPG_F_N2) ? 1u : 0u);
+			if (r.flags & SPG_F_INSERT) atomicAdd(&cnt[0], 2u);
+			if (r.flags & SPG_F_ADAPTER) atomicAdd(&cnt[1], 2u);
+			if (tq) atomicAdd(&cnt[2], tq);
+			if (tn) atomicAdd(&cnt[3], tn);
+			if (removed) atomicAdd(&cnt[4], removed);
+			atomicAdd(&h_rem[min(l1, SPG_MAXLEN - 1)], 1u);
+			atomicAdd(&h_rem[min(l2, SPG_MAXLEN - 1)], 1u);
+			if (o1 > l1) atomicAdd(&h_trim[min(o1, SPG_MAXLEN - 1)], (uint32_t)(o1 - l1));
+			if (o2 > l2) atomicAdd(&h_trim[min(o2, SPG_MAXLEN - 1)], (uint32_t)(o2 - l2));
+		}
+		__syncthreads();
+		if (threadIdx.x < 5 && cnt[threadIdx.x]) atomicAdd(&A.stats[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+		for (int i = threadIdx.x; i < SPG_MAXLEN; i += kFqOutPairs)
+		{
+			if (h_rem[i]) atomicAdd(&A.stats[5 + i], (unsigned long long)h_rem[i]);
+			if (h_trim[i]) atomicAdd(&A.stats[5 + SPG_MAXLEN + i], (unsigned long long)h_trim[i]);
+		}
+	}
 }
 
 // one CTA of 1024 threads: exclusive scan of the per-CTA byte counts of the four streams; totals into the plan

@@ -24,7 +24,11 @@ constexpr int kQcLen = 8;                          // [SPG_MAXLEN] read length h
 constexpr int kQcPile = kQcLen + SPG_MAXLEN;       // [SPG_MAXLEN][5]
 constexpr int kQcQf = kQcPile + 5 * SPG_MAXLEN;    // [SPG_MAXLEN] quality sums, forward reads
 constexpr int kQcQr = kQcQf + SPG_MAXLEN;          // [SPG_MAXLEN] reverse reads
-constexpr int kQcWords = kQcQr + SPG_MAXLEN;
+constexpr int kQcBaseQual = kQcQr + SPG_MAXLEN;    // [100] bases by quality
+constexpr int kQcReadQual = kQcBaseQual + 100;     // [100] reads by rounded mean quality
+constexpr int kQcDistF = kQcReadQual + 100;        // [60] Histogram(0,60,1) of the mean quality, forward reads
+constexpr int kQcDistR = kQcDistF + 60;            // [60] reverse reads
+constexpr int kQcWords = kQcDistR + 60;
 
 struct QcArgs
 {
@@ -42,8 +46,21 @@ struct QcArgs
 	unsigned long long* acc; // [kQcWords]
 	int forward_only; // rows of read 2 are not read, nothing is counted as reverse read (single-end input)
 	int strict;       // FastqEntry::validate: bases of exactly A,C,G,T,N, qualities of 33..74 only
+	int plots;        // also fill the histograms behind the qcML plots (bases by quality, reads by mean quality): one shared-memory atomic per 32 bases
 	int* bad_flag;    // if not null: set to 1 when this launch met a character that counts in `errors` (per-chunk report of the FASTQ stream)
+	uint8_t bin_of_int[100]; // bin of Histogram(0,60,1) for an integral mean quality k (host-evaluated double expression)
 };
+
+// The two per-read bins of the plots from the read's integer quality sum and length (len > 0): index of read_qualities_
+// (std::round(sum/len), ties away from zero) and bin of qscore_dist (floor(sum/len / 60 * 60) in double). Both double expressions
+// only depend on the exact quotient unless it is an integer (a non-integral quotient with a denominator below 1000 is more than
+// 1e-3 away from the next integer, far beyond the rounding of two double operations), so integers and the 100-entry table do.
+__device__ __forceinline__ void qc_read_bins(const QcArgs& A, int total, int len, int& rq, int& bin)
+{
+	const int k = total / len, rem = total - k * len;
+	rq = (2 * total + len) / (2 * len);
+	bin = rem == 0 ? (int)A.bin_of_int[min(k, 99)] : min(k, 59);
+}
 
 constexpr uint32_t kQcBad = 0x80000000u;
 
@@ -86,6 +103,7 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 	__shared__ uint32_t lutb[256], lutq[256];
 	__shared__ uint32_t s_len[SPG_MAXLEN];
 	__shared__ uint32_t s_acc[7][NW * 32]; // [A,C,G,T,N,qsum_f,qsum_r][cycle] of this CTA
+	__shared__ uint32_t s_hist[320];       // base_qualities[100] | read_qualities[100] | qscore_dist forward[60] | reverse[60]
 	__shared__ unsigned long long s_scalar[8];
 
 	const int warp = threadIdx.x >> 5;
@@ -104,6 +122,7 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 	}
 	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads) s_len[i] = 0;
 	for (int i = threadIdx.x; i < 7 * NW * 32; i += kThreads) (&s_acc[0][0])[i] = 0;
+	for (int i = threadIdx.x; i < 320; i += kThreads) s_hist[i] = 0;
 	if (threadIdx.x < 8) s_scalar[threadIdx.x] = 0;
 	if (threadIdx.x == 0)
 	{
@@ -153,6 +172,19 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 		unsigned long long bases = 0;
 		uint32_t reads = 0, rq20 = 0; // warp-uniform, reported by lane 0
 		int since_flush = 0;
+		// the per-read bins of the plots need two integer divisions: lane k keeps (quality sum, length, direction) of the k-th read
+		// since the last round and all lanes divide at once every 32 reads
+		int st_total = 0, st_len = 0, st_n = 0;
+		auto read_bins = [&]() {
+			if (lane < st_n && st_len > 0)
+			{
+				int rq, bin;
+				qc_read_bins(A, st_total & 0x7FFFFFFF, st_len, rq, bin);
+				if (rq < 100) atomicAdd(&s_hist[100 + rq], 1u);
+				atomicAdd(&s_hist[(st_total < 0 ? 260 : 200) + bin], 1u); // bit 31 of the stashed sum: reverse read
+			}
+			st_n = 0;
+		};
 
 		auto flush = [&]() {
 #pragma unroll
@@ -207,6 +239,7 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 						if (pos < len)
 						{
 							const uint32_t vb = lutb[lds_u8(rb + pos)], vq = lutq[lds_u8(rq + pos)];
+							if (A.plots && !(vq & kQcBad)) atomicAdd(&s_hist[vq & 0x7Fu], 1u); // base_qualities_[q]++
 							bad |= vb | vq; // only bit 31 is looked at
 							pk[w] += vb;    // a bad base adds bit 31, which no field uses
 							racc += vq;
@@ -218,6 +251,15 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 					const int total = __reduce_add_sync(kFull, (int)(racc & 0xFFFu));
 					// mean_qscore = q_sum/cycles >= 20.0 (only if cycles > 0: 0/0 is not a valid float there)
 					if (len > 0 && total >= 20 * len) ++rq20;
+					if (A.plots)
+					{
+						if (lane == st_n)
+						{
+							st_total = total | (rd ? (int)0x80000000 : 0);
+							st_len = len;
+						}
+						if (++st_n == 32) read_bins();
+					}
 				}
 				++reads;
 				if (++since_flush == 31) flush(); // 2 reads x 31 pairs = 62 < 64: the 6-bit fields cannot overflow
@@ -230,6 +272,7 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 			}
 		}
 		flush();
+		read_bins();
 		const unsigned long long t20 = __reduce_add_sync(kFull, c20), t30 = __reduce_add_sync(kFull, c30);
 		const bool any_bad = __any_sync(kFull, (bad & kQcBad) != 0);
 		if (lane == 0)
@@ -250,6 +293,8 @@ __global__ void __launch_bounds__((CW + 1) * 32) qc_kernel(const __grid_constant
 	if (threadIdx.x < 8 && s_scalar[threadIdx.x]) atomicAdd(&A.acc[threadIdx.x], s_scalar[threadIdx.x]);
 	for (int i = threadIdx.x; i < SPG_MAXLEN; i += kThreads)
 		if (s_len[i]) atomicAdd(&A.acc[kQcLen + i], (unsigned long long)s_len[i]);
+	for (int i = threadIdx.x; i < 320; i += kThreads)
+		if (s_hist[i]) atomicAdd(&A.acc[kQcBaseQual + i], (unsigned long long)s_hist[i]); // the four histograms are laid out in the same order
 	for (int i = threadIdx.x; i < 7 * NW * 32; i += kThreads)
 	{
 		const int k = i / (NW * 32), cycle = i % (NW * 32);
@@ -290,6 +335,7 @@ __global__ void __launch_bounds__(256) qc_kernel_generic(const __grid_constant__
 				const int qv = (int)(signed char)qrow[pos] - 33;
 				atomicAdd(&A.acc[(rd ? kQcQr : kQcQf) + pos], (unsigned long long)qv);
 				rsum += qv;
+				if (A.plots) atomicAdd(&A.acc[kQcBaseQual + qv], 1ull);
 				n20 += (vq >> 12) & 1u;
 				n30 += (vq >> 20) & 1u;
 			}
@@ -302,6 +348,13 @@ __global__ void __launch_bounds__(256) qc_kernel_generic(const __grid_constant__
 				atomicAdd(&A.acc[kQcBases], (unsigned long long)len);
 				if (len < SPG_MAXLEN) atomicAdd(&A.acc[kQcLen + len], 1ull);
 				if (len > 0 && total >= 20 * len) atomicAdd(&A.acc[kQcReadQ20], 1ull);
+				if (A.plots && len > 0 && !any_bad)
+				{
+					int rq, bin;
+					qc_read_bins(A, total, len, rq, bin);
+					if (rq < 100) atomicAdd(&A.acc[kQcReadQual + rq], 1ull);
+					atomicAdd(&A.acc[(rd ? kQcDistR : kQcDistF) + bin], 1ull);
+				}
 				atomicAdd(&A.acc[kQcBaseQ20], (unsigned long long)t20);
 				atomicAdd(&A.acc[kQcBaseQ30], (unsigned long long)t30);
 				if (any_bad) atomicAdd(&A.acc[kQcErrors], 1ull);

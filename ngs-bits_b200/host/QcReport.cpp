@@ -111,6 +111,16 @@ void qcAccumulate(spg_qc_stats& a, const spg_qc_stats& b)
 		a.qsum_forward[i] += b.qsum_forward[i];
 		a.qsum_reverse[i] += b.qsum_reverse[i];
 	}
+	for (int i = 0; i < 100; ++i)
+	{
+		a.base_qualities[i] += b.base_qualities[i];
+		a.read_qualities[i] += b.read_qualities[i];
+	}
+	for (int i = 0; i < 60; ++i)
+	{
+		a.qscore_dist_forward[i] += b.qscore_dist_forward[i];
+		a.qscore_dist_reverse[i] += b.qscore_dist_reverse[i];
+	}
 }
 
 void storeQcML(const std::string& filename, const spg_qc_stats& stats, const std::vector<std::string>& source_files, const std::string& parameters, const std::string& software)

@@ -165,33 +165,20 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 		}
 		if (o.n_pairs != f.a->records || (size_t)o.consumed1 != f.a->data.size() || (size_t)o.consumed2 != f.b->data.size())
 			throw ProgrammingException("the device framed the chunk differently from the reader");
-		// statistics (OutputWorker.cpp:36-77) from the result records
-		const int min_len = std::max(params.min_len, 0);
-		long long removed = 0, t_insert = 0, t_adapter = 0, t_q = 0, t_n = 0;
-		for (int r = 0; r < o.n_pairs; ++r)
+		// statistics (OutputWorker.cpp:59-77): reduced on the device from the result records (spg_fq_stats)
+		if (!o.stats) throw ProgrammingException("the stream did not return summary counters");
+		const spg_fq_stats& st = *o.stats;
+		for (int len = 0; len < SPG_MAXLEN; ++len)
 		{
-			const spg_result& k = o.results[r];
-			if (k.flags & SPG_F_INSERT) t_insert += 2;
-			if (k.flags & SPG_F_ADAPTER) t_adapter += 2;
-			t_q += ((k.flags & SPG_F_Q1) ? 1 : 0) + ((k.flags & SPG_F_Q2) ? 1 : 0);
-			t_n += ((k.flags & SPG_F_N1) ? 1 : 0) + ((k.flags & SPG_F_N2) ? 1 : 0);
-			const bool ok1 = (int)k.len1 >= min_len, ok2 = (int)k.len2 >= min_len;
-			if (ok1 && ok2) {}
-			else if (singles && ok1) removed += 1;
-			else if (singles && ok2) removed += 1;
-			else removed += 2;
-			stats.bases_remaining[k.len1] += 1;
-			stats.bases_remaining[k.len2] += 1;
-			const int o1 = o.len1[r], o2 = o.len2[r];
-			if (o1 > 0) stats.bases_perc_trim_sum += (double)(o1 - (int)k.len1) / o1;
-			if (o2 > 0) stats.bases_perc_trim_sum += (double)(o2 - (int)k.len2) / o2;
+			if (st.bases_remaining[len]) stats.bases_remaining[len] += (double)st.bases_remaining[len];
+			if (len > 0 && st.trimmed_bases_by_length[len]) stats.bases_perc_trim_sum += (double)st.trimmed_bases_by_length[len] / len;
 		}
 		stats.read_num += 2LL * o.n_pairs;
-		stats.reads_trimmed_insert += (double)t_insert;
-		stats.reads_trimmed_adapter += (double)t_adapter;
-		stats.reads_trimmed_q += (double)t_q;
-		stats.reads_trimmed_n += (double)t_n;
-		stats.reads_removed += (double)removed;
+		stats.reads_trimmed_insert += (double)st.reads_trimmed_insert;
+		stats.reads_trimmed_adapter += (double)st.reads_trimmed_adapter;
+		stats.reads_trimmed_q += (double)st.reads_trimmed_q;
+		stats.reads_trimmed_n += (double)st.reads_trimmed_n;
+		stats.reads_removed += (double)st.reads_removed;
 		t_stats += since(t0);
 		t0 = clk::now();
 		for (int k = 0; k < 4; ++k)

@@ -55,6 +55,7 @@ class _QcStats(C.Structure):
         ("base_q20", C.c_int64), ("base_q30", C.c_int64), ("errors", C.c_int64),
         ("read_lengths", C.c_int64 * MAXLEN), ("pileup", (C.c_int64 * 5) * MAXLEN),
         ("qsum_forward", C.c_int64 * MAXLEN), ("qsum_reverse", C.c_int64 * MAXLEN),
+        ("base_qualities", C.c_int64 * 100), ("read_qualities", C.c_int64 * 100), ("qscore_dist_forward", C.c_int64 * 60), ("qscore_dist_reverse", C.c_int64 * 60),
     ]
 
 
@@ -65,6 +66,8 @@ def qc_stats_to_dict(st):
     d["pileup"] = np.array([list(row) for row in st.pileup], dtype=np.int64)
     d["qsum_forward"] = np.array(st.qsum_forward, dtype=np.int64)
     d["qsum_reverse"] = np.array(st.qsum_reverse, dtype=np.int64)
+    for k in ("base_qualities", "read_qualities", "qscore_dist_forward", "qscore_dist_reverse"):  # the accumulators behind the qcML plots
+        d[k] = np.array(getattr(st, k), dtype=np.int64)
     return d
 
 
@@ -197,7 +200,12 @@ class _FqInput(C.Structure):
 class _FqOutput(C.Structure):
     _fields_ = [("n_pairs", C.c_int32), ("records1", C.c_int32), ("records2", C.c_int32), ("consumed1", C.c_int64), ("consumed2", C.c_int64),
                 ("out", C.c_void_p * 4), ("out_bytes", C.c_int64 * 4), ("results", C.c_void_p), ("len1", C.c_void_p), ("len2", C.c_void_p),
-                ("frame_status", C.c_void_p), ("error_pair", C.c_int32), ("max_len", C.c_int32), ("invalid_chars", C.c_int32)]
+                ("frame_status", C.c_void_p), ("error_pair", C.c_int32), ("max_len", C.c_int32), ("invalid_chars", C.c_int32), ("stats", C.c_void_p)]
+
+
+class _FqStats(C.Structure):
+    _fields_ = [("reads_trimmed_insert", C.c_int64), ("reads_trimmed_adapter", C.c_int64), ("reads_trimmed_q", C.c_int64), ("reads_trimmed_n", C.c_int64),
+                ("reads_removed", C.c_int64), ("bases_remaining", C.c_int64 * MAXLEN), ("trimmed_bases_by_length", C.c_int64 * MAXLEN)]
 
 
 _lib.spg_fq_open.argtypes = [C.c_void_p, C.POINTER(_FqConfig), C.POINTER(C.c_void_p)]
@@ -338,6 +346,12 @@ class FastqChunk:
         self.len2 = _np_view(o.len2, (n,), np.uint16).copy() if n else np.zeros(0, np.uint16)
         self.frame_status = _np_view(o.frame_status, (n,), np.uint8).copy() if n else np.zeros(0, np.uint8)
         self.error_pair, self.max_len, self.invalid_chars = o.error_pair, o.max_len, o.invalid_chars
+        self.stats = None  # summary counters of the chunk (spg_fq_stats) as a dict
+        if o.stats:
+            st = _FqStats.from_address(o.stats)
+            self.stats = {k: int(getattr(st, k)) for k in ("reads_trimmed_insert", "reads_trimmed_adapter", "reads_trimmed_q", "reads_trimmed_n", "reads_removed")}
+            self.stats["bases_remaining"] = np.array(st.bases_remaining, dtype=np.int64)
+            self.stats["trimmed_bases_by_length"] = np.array(st.trimmed_bases_by_length, dtype=np.int64)
 
 
 class FastqStream:

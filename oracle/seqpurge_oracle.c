@@ -551,12 +551,25 @@ static void qc_update(const uint8_t* bases, const uint8_t* quals, int cycles, in
 		}
 		if (q >= 20.0) ++s->base_q20;
 		if (q >= 30.0) ++s->base_q30;
+		s->base_qualities[q]++; /* :61 */
 		if (reverse) s->qsum_reverse[i] += q;
 		else s->qsum_forward[i] += q;
 	}
 	double mean_qscore = q_sum / cycles; /* :71-80 */
 	if (isfinite(mean_qscore))
 	{
+		long rq = (long)round(mean_qscore); /* :74 read_qualities_[std::round(mean_qscore)]++ */
+		if (rq >= 0 && rq < 100) s->read_qualities[rq]++;
+		else s->errors++;
+		/* :76-77 Histogram(0, 60, 1)::inc(mean, true): index = floor((val-min_) / (max_-min_) * bins_.size()), bounded to the bins
+		   (src/cppCORE/Histogram.cpp:117-126) */
+		const double hmin = 0.0, hmax = 60.0;
+		const long nbins = 60;
+		long bi = (long)floor((mean_qscore - hmin) / (hmax - hmin) * nbins);
+		if (bi < 0) bi = 0;
+		if (bi > nbins - 1) bi = nbins - 1;
+		if (reverse) s->qscore_dist_reverse[bi]++;
+		else s->qscore_dist_forward[bi]++;
 		if (mean_qscore >= 20.0) ++s->read_q20;
 	}
 }

@@ -85,6 +85,11 @@ typedef struct spo_qc_stats
 	int64_t pileup[SPO_MAXLEN][5]; /* A C G T N */
 	int64_t qsum_forward[SPO_MAXLEN];
 	int64_t qsum_reverse[SPO_MAXLEN];
+	/* the accumulators behind the three qcML plots (StatisticsReads.cpp:60-61,74-77) */
+	int64_t base_qualities[100];      /* base_qualities_[q] */
+	int64_t read_qualities[100];      /* read_qualities_[round(mean q of the read)] */
+	int64_t qscore_dist_forward[60];  /* qscore_dist_r1: Histogram(0, 60, 1) of the mean quality of forward reads */
+	int64_t qscore_dist_reverse[60];  /* qscore_dist_r2 */
 } spo_qc_stats;
 
 /* StatisticsReads::update for read 1 (FORWARD) and read 2 (REVERSE) of every pair of a SoA batch, added to *out */

@@ -34,6 +34,7 @@ class _SpoQc(C.Structure):
         ("base_q20", C.c_int64), ("base_q30", C.c_int64), ("errors", C.c_int64),
         ("read_lengths", C.c_int64 * MAXLEN), ("pileup", (C.c_int64 * 5) * MAXLEN),
         ("qsum_forward", C.c_int64 * MAXLEN), ("qsum_reverse", C.c_int64 * MAXLEN),
+        ("base_qualities", C.c_int64 * 100), ("read_qualities", C.c_int64 * 100), ("qscore_dist_forward", C.c_int64 * 60), ("qscore_dist_reverse", C.c_int64 * 60),
     ]
 
 
@@ -43,6 +44,8 @@ def _qc_to_dict(st):
     d["pileup"] = np.array([list(row) for row in st.pileup], dtype=np.int64)
     d["qsum_forward"] = np.array(st.qsum_forward, dtype=np.int64)
     d["qsum_reverse"] = np.array(st.qsum_reverse, dtype=np.int64)
+    for k in ("base_qualities", "read_qualities", "qscore_dist_forward", "qscore_dist_reverse"):
+        d[k] = np.array(getattr(st, k), dtype=np.int64)
     return d
 
 

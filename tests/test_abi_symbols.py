@@ -66,7 +66,7 @@ def test_ctypes_structs_have_the_sizes_the_compiler_gives_the_header(tmp_path):
     import seqpurge_b200 as sp
 
     pairs = {"spg_params": sp._Params, "spg_slot_view": sp._SlotView, "spg_ec_stats": sp._EcStats, "spg_qc_stats": sp._QcStats, "spg_fq_config": sp._FqConfig,
-             "spg_fq_input": sp._FqInput, "spg_fq_output": sp._FqOutput, "spg_synth_config": sp._SynthConfig}
+             "spg_fq_input": sp._FqInput, "spg_fq_output": sp._FqOutput, "spg_fq_stats": sp._FqStats, "spg_synth_config": sp._SynthConfig}
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "seqpurge_b200.h"\nint main(void){' + "".join(f'printf("{n} %zu\\n", sizeof({n}));' for n in pairs) + "return 0;}\n")
     exe = tmp_path / "sizes"

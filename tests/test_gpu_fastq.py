@@ -213,6 +213,32 @@ def test_consensus_counters_and_records(sp):  # noqa: F811
     assert not unknown and np.array_equal(counts, exp)
 
 
+@pytest.mark.parametrize("singles,min_len", [(False, 30), (True, 60), (True, 0)])
+def test_summary_counters_on_the_device(sp, singles, min_len):  # noqa: F811
+    """spg_fq_stats (the counters OutputWorker::run adds to TrimmingStatistics, OutputWorker.cpp:59-77) of every chunk against a
+    direct restatement over the chunk's result records and untrimmed lengths."""
+    t1, t2 = gz(f"{G}/SeqPurge_in1.fastq.gz"), gz(f"{G}/SeqPurge_in2.fastq.gz")
+    params = dict(qcut=20, ncut=3)
+    outs, chunks, _, _ = run_stream(sp, t1, t2, params, min_len, singles, max_pairs=700)
+    assert sum(c.n_pairs for c in chunks) == 2502
+    for c in chunks:
+        st, r = c.stats, c.results
+        assert st is not None
+        assert st["reads_trimmed_insert"] == 2 * int(((r["flags"] & 1) != 0).sum())
+        assert st["reads_trimmed_adapter"] == 2 * int(((r["flags"] & 2) != 0).sum())
+        assert st["reads_trimmed_q"] == int(((r["flags"] & 4) != 0).sum() + ((r["flags"] & 8) != 0).sum())
+        assert st["reads_trimmed_n"] == int(((r["flags"] & 16) != 0).sum() + ((r["flags"] & 32) != 0).sum())
+        ok1, ok2 = r["len1"] >= min_len, r["len2"] >= min_len
+        removed = np.where(ok1 & ok2, 0, np.where((ok1 | ok2) & singles, 1, 2))
+        assert st["reads_removed"] == int(removed.sum())
+        rem = np.bincount(np.concatenate([r["len1"], r["len2"]]).astype(np.int64), minlength=1000)
+        assert np.array_equal(st["bases_remaining"], rem)
+        trimmed = np.zeros(1000, np.int64)
+        np.add.at(trimmed, c.len1.astype(np.int64), c.len1.astype(np.int64) - r["len1"])
+        np.add.at(trimmed, c.len2.astype(np.int64), c.len2.astype(np.int64) - r["len2"])
+        assert np.array_equal(st["trimmed_bases_by_length"], trimmed)
+
+
 def test_synthetic_20k_pairs_against_the_oracle_cli(sp, oracle_build, tmp_path):  # noqa: F811
     import torch
 

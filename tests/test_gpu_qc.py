@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 
 G = H.GOLDEN
 FIELDS = ("reads_forward", "reads_reverse", "bases_sequenced", "read_q20", "base_q20", "base_q30")
-ARRAYS = ("read_lengths", "pileup", "qsum_forward", "qsum_reverse")
+ARRAYS = ("read_lengths", "pileup", "qsum_forward", "qsum_reverse", "base_qualities", "read_qualities", "qscore_dist_forward", "qscore_dist_reverse")
 
 
 def assert_qc_equal(got, want):
@@ -30,10 +30,13 @@ def assert_qc_equal(got, want):
     assert got["errors"] == 0 and want["errors"] == 0
 
 
+# spg_params.qc = 5: the statistics (1) with the histograms behind the qcML plots (+4), so that every accumulator is compared
+
+
 def qc_via_submit(sp, batch, chunk=None, n_slots=2, **params):  # noqa: F811
     """-qc on the slot path: H2D, qc_kernel on the raw reads, then the trimming kernel (which may edit them with -ec)."""
     chunk = chunk or batch.n
-    eng = sp.Engine(sp.TrimmingParameters(qc=True, **params), devices=(0,), n_slots=n_slots, max_pairs=chunk, max_len=min(batch.stride, 999))
+    eng = sp.Engine(sp.TrimmingParameters(qc=5, **params), devices=(0,), n_slots=n_slots, max_pairs=chunk, max_len=min(batch.stride, 999))
     out = np.zeros(batch.n, sp.RESULT_DTYPE)
     pending = []
     for k, st in enumerate(range(0, batch.n, chunk)):
@@ -63,7 +66,7 @@ def qc_via_device(sp, batch):  # noqa: F811
     t = {k: torch.from_numpy(getattr(batch, k)).to(dev) for k in ("bases1", "quals1", "bases2", "quals2")}
     l1 = torch.from_numpy(batch.len1.view(np.int16)).to(dev)
     l2 = torch.from_numpy(batch.len2.view(np.int16)).to(dev)
-    eng = sp.Engine(sp.TrimmingParameters(qc=True), devices=(0,))
+    eng = sp.Engine(sp.TrimmingParameters(qc=5), devices=(0,))
     eng.qc_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, n_pairs=batch.n)  # Batch rows are padded to a multiple of 8
     got = eng.qc_stats()
     eng.close()
@@ -124,7 +127,7 @@ def test_accumulates_over_calls_and_quality_extremes(sp):  # noqa: F811
     want = H.oracle_qc(batch)
     assert want["errors"] == 0
     dev = torch.device("cuda:0")
-    eng = sp.Engine(sp.TrimmingParameters(qc=True), devices=(0,))
+    eng = sp.Engine(sp.TrimmingParameters(qc=5), devices=(0,))
     for st in range(0, batch.n, 1000):
         t = [torch.from_numpy(np.ascontiguousarray(getattr(batch, k)[st : st + 1000])).to(dev) for k in ("bases1", "quals1", "bases2", "quals2")]
         l1 = torch.from_numpy(batch.len1[st : st + 1000].view(np.int16)).to(dev)
@@ -158,7 +161,7 @@ def test_synthetic_config2_slice(sp):  # noqa: F811
     l1 = torch.empty(n, dtype=torch.int16, device=dev)
     l2 = torch.empty(n, dtype=torch.int16, device=dev)
     sp.synth_device(cfg, 0, n, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
-    eng = sp.Engine(sp.TrimmingParameters(qc=True), devices=(0,))
+    eng = sp.Engine(sp.TrimmingParameters(qc=5), devices=(0,))
     eng.qc_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
     got = eng.qc_stats()
     eng.close()
@@ -197,3 +200,24 @@ def test_cli_qcml_equals_reference_golden(sp, tmp_path):  # noqa: F811
 
     for mine, gold in (("o1", 1), ("o2", 2)):
         assert gzip.open(tmp_path / f"{mine}.fastq.gz").read() == gzip.open(f"{G}/SeqPurge_out{gold}.fastq.gz").read()
+
+
+def test_plot_histograms_are_opt_in(sp):  # noqa: F811
+    """spg_params.qc = 1 leaves the plot histograms alone (they cost an atomic per 32 bases); everything else is unchanged."""
+    batch = H.random_batch(800, 150, seed=3)
+    eng = sp.Engine(sp.TrimmingParameters(qc=1), devices=(0,), n_slots=1, max_pairs=batch.n, max_len=batch.stride)
+    s = eng.slot(0)
+    for name in ("bases1", "quals1", "bases2", "quals2"):
+        getattr(s, name)[: batch.n] = getattr(batch, name)[: batch.n]
+    s.len1[: batch.n] = batch.len1[: batch.n]
+    s.len2[: batch.n] = batch.len2[: batch.n]
+    eng.submit(0, batch.n)
+    eng.wait(0)
+    got, want = eng.qc_stats(), H.oracle_qc(batch)
+    eng.close()
+    for k in FIELDS:
+        assert got[k] == want[k], k
+    for k in ("read_lengths", "pileup", "qsum_forward", "qsum_reverse"):
+        assert np.array_equal(got[k], want[k]), k
+    for k in ("base_qualities", "read_qualities", "qscore_dist_forward", "qscore_dist_reverse"):
+        assert not got[k].any(), k
