@@ -43,6 +43,9 @@ CONFIGS = {
                params=dict(qcut=15, ncut=7), desc="C4: synthetic 2x150bp pairs, 2% substitutions, low-quality tails of mean 20, N runs in 0.5% of reads, -qcut 15 -ncut 7"),
     "C5": dict(read_len=150, synth=dict(insert_mean=350.0, insert_sd=100.0, error_rate=0.002, n_rate=1e-4, lowq_tail_mean=2.0, binned_quals=True), params=dict(),
                desc="C5: synthetic 2x150bp NovaSeq-like pairs, insert~N(350,100), binned qualities, SeqPurge defaults"),
+    # not a BASELINE config: long reads (the widest plane variant of the warp-per-pair kernel), for `--only L600`
+    "L600": dict(read_len=600, synth=dict(insert_mean=500.0, insert_sd=200.0, error_rate=0.005, n_rate=1e-4, lowq_tail_mean=10.0), params=dict(),
+                 desc="synthetic 2x600bp pairs, insert~N(500,200) (reads beyond the register-plane widths of round 1)"),
 }
 
 

@@ -221,7 +221,7 @@ struct Device
 		size_t smem = 0;      // launch geometry the cached value belongs to (0: none yet)
 		int ctas = 0;
 	};
-	Occ occ[4][3];      // NW = 0,5,8,10 x kernel variant (min blocks 2,3,4)
+	Occ occ[6][3];      // NW = 0,5,8,10,16,32 x kernel variant (min blocks 2,3,4; the two long-read widths have one variant each)
 	Occ full_occ[4][9]; // the variants compiled for one read length (full_index)
 	Occ lane_occ[4][9]; // the lane-per-pair kernels of the same read lengths
 	Occ qc_occ[3];      // qc_kernel, NW = 5,8,10
@@ -303,8 +303,11 @@ int fail(spg_ctx* ctx, int code, const std::string& msg)
 		if (e_ != cudaSuccess) return fail(ctx, SPG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));    \
 	} while (0)
 
-int nw_for_stride(int stride) { return stride <= 160 ? 5 : stride <= 256 ? 8 : stride <= 320 ? 10 : 0; }
-int nw_index(int nw) { return nw == 5 ? 1 : nw == 8 ? 2 : nw == 10 ? 3 : 0; }
+// plane words per read of the trimming kernels: rows of up to 160 / 256 / 320 bytes keep a read in 5 / 8 / 10 registers per plane;
+// longer rows (up to MAXLEN-1 = 999 bases) use 16 or 32 words (more registers, fewer resident warps, still bit planes instead of bytes)
+int nw_for_stride(int stride) { return stride <= 160 ? 5 : stride <= 256 ? 8 : stride <= 320 ? 10 : stride <= 512 ? 16 : stride <= 1024 ? 32 : 0; }
+int nw_index(int nw) { return nw == 5 ? 1 : nw == 8 ? 2 : nw == 10 ? 3 : nw == 16 ? 4 : nw == 32 ? 5 : 0; }
+int nw_for_qc(int stride) { return stride <= 320 ? nw_for_stride(stride) : 0; } // the statistics kernel keeps its generic form beyond 320
 
 void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 {
@@ -315,6 +318,11 @@ void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 	if (tp > 48) tp = 48;
 	tile_pairs = tp;
 	stages = 2;
+	if (stride > 320) // long reads (16 / 32 plane words, one or two resident CTAs): two pairs per warp and tile, one more tile in flight
+	{
+		tile_pairs = 16;
+		stages = 3;
+	}
 	smem = (size_t)stages * (4 * (size_t)tp * stride + 4 * (size_t)tp);
 }
 
@@ -606,6 +614,8 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 		case 5: e = launch_nw<5>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ, ctx->mu); break;
 		case 8: e = launch_nw<8>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ, ctx->mu); break;
 		case 10: e = launch_nw<10>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ, ctx->mu); break;
+		case 16: e = launch_cfg<16, 2>(a, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, &d.occ[4][0], ctx->mu); break;
+		case 32: e = launch_cfg<32, 1>(a, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, &d.occ[5][0], ctx->mu); break;
 		default: e = launch_nw<0>(a, cw, d.sm_count, ctx->ctas_per_sm, n_tiles, smem, stream, occ, ctx->mu); break;
 	}
 	if (e != cudaSuccess) return fail(ctx, SPG_ERR_CUDA, std::string("trim_kernel launch: ") + cudaGetErrorString(e));
@@ -663,7 +673,7 @@ int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, con
 		a.bin_of_int[k] = (uint8_t)std::min(59L, std::max(0L, b));
 	}
 	cudaError_t e = cudaSuccess;
-	switch (nw_for_stride(stride))
+	switch (nw_for_qc(stride))
 	{
 		case 5: e = launch_qc_cfg<5>(a, d.sm_count, stream, &d.qc_occ[0], ctx->mu); break;
 		case 8: e = launch_qc_cfg<8>(a, d.sm_count, stream, &d.qc_occ[1], ctx->mu); break;
@@ -1085,7 +1095,7 @@ int spg_last_kernel(spg_ctx* ctx, char* name, int cap)
 	{
 		if (v == 0) snprintf(name, (size_t)cap, "none");
 		else if (layout == 2) snprintf(name, (size_t)cap, "spg::trim_lanes_kernel<NW=%d,FULL=%d,CW=%d,MINB=%d>", nw, full, nw <= 5 ? LaneCfg<5>::CW : LaneCfg<8>::CW, nw <= 5 ? LaneCfg<5>::MINB : LaneCfg<8>::MINB);
-		else snprintf(name, (size_t)cap, "spg::trim_kernel<NW=%d,CW=%d,MINB=%d,FULL=%d>", nw, kCW, ctx->min_blocks, layout == 1 ? full : 0);
+		else snprintf(name, (size_t)cap, "spg::trim_kernel<NW=%d,CW=%d,MINB=%d,FULL=%d>", nw, kCW, nw == 16 ? 2 : nw == 32 ? 1 : ctx->min_blocks, layout == 1 ? full : 0);
 	}
 	return v;
 }

@@ -805,9 +805,9 @@ __device__ __forceinline__ int adapter_scan_planes(const KArgs& A, const SmemTab
 {
 	const int full = HASN ? 0 : (len - 31 - A.a_size >= 0 ? ((len - 31 - A.a_size) >> 5) + 1 : 0); // warp-uniform
 	uint32_t pm;
-	static_assert(NW <= 10, "extend the dispatch");
 #define SPG_SCAN(QF) pm = adapter_scan_rounds<NW, HASN, (QF) <= NW ? (QF) : NW>(A, T, sh, sl, sn, len, ah, al, an, amask, pass_by_mm, lane)
-	switch (full)
+	if (NW > 10) SPG_SCAN(0); // long reads (16 / 32 plane words): every round takes the masked form, no dispatch on the read length
+	else switch (full)
 	{
 		case 0: SPG_SCAN(0); break;
 		case 1: SPG_SCAN(1); break;
