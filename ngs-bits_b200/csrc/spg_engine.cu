@@ -318,11 +318,7 @@ void tile_geometry(int stride, int& tile_pairs, int& stages, size_t& smem)
 	if (tp > 48) tp = 48;
 	tile_pairs = tp;
 	stages = 2;
-	if (stride > 320) // long reads (16 / 32 plane words, one or two resident CTAs): two pairs per warp and tile, one more tile in flight
-	{
-		tile_pairs = 16;
-		stages = 3;
-	}
+
 	smem = (size_t)stages * (4 * (size_t)tp * stride + 4 * (size_t)tp);
 }
 

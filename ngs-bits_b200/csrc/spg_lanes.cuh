@@ -31,6 +31,15 @@ __device__ __forceinline__ uint32_t lds_u32_at(uint32_t a)
 	asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
 	return v;
 }
+// a load from a table that is written once at kernel start (behind a __syncthreads): not volatile, so that the compiler may move it
+// ahead of the arithmetic that precedes its use
+template <int OFF>
+__device__ __forceinline__ int lds_s16_const_at(uint32_t a)
+{
+	int v;
+	asm("ld.shared.s16 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF));
+	return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
 {
 	uint32_t v;
@@ -194,6 +203,16 @@ __device__ __forceinline__ void lane_reversed(const uint32_t (&acc)[NW], uint32_
 		const uint32_t hi = i1 < NW ? acc[NW - 1 - (i1 < NW ? i1 : 0)] : 0u;
 		r[w] = __funnelshift_r(lo, hi, bs) & low_mask_const(FULL - 32 * w);
 	}
+}
+
+// the FULL-bit string of a plane the other way round (forward <-> reversed read), both left aligned
+template <int NW, int FULL>
+__device__ __forceinline__ void lane_flip(const uint32_t (&in)[NW], uint32_t (&out)[NW])
+{
+	uint32_t acc[NW];
+#pragma unroll
+	for (int w = 0; w < NW; ++w) acc[w] = __brev(in[w]);
+	lane_reversed<NW, FULL>(acc, 0u, out);
 }
 
 // 32 bits of a plane copy starting at bit `pos` (0 <= pos < 32*NW); plane: shared address of word 0 of this lane
@@ -863,7 +882,7 @@ __device__ __noinline__ uint32_t lane_tile_n(const KArgs& A, const SmemTables& T
 		plain = (ent.y & 0xFFFFu) == (uint32_t)FULL && (ent.y >> 16) == (uint32_t)FULL;
 	}
 	const bool member = lane < n_entries;
-	uint32_t f1h[NW], f1l[NW], n1[NW], f2h[NW], f2l[NW], n2[NW], r2h[NW], r2l[NW], n2r[NW];
+	uint32_t f1h[NW], f1l[NW], n1[NW], r2h[NW], r2l[NW], n2r[NW];
 	{
 		uint32_t acch[NW], accl[NW], accn[NW];
 		const size_t goff = (size_t)p * A.stride;
@@ -874,9 +893,6 @@ __device__ __noinline__ uint32_t lane_tile_n(const KArgs& A, const SmemTables& T
 		lane_forward<NW, FULL>(accl, odd1, f1l);
 		lane_forward<NW, FULL>(accn, odd1, n1);
 		if (plain) bad |= lane_pack_global<NW, FULL>(A.b2 + goff, acch, accl, accn);
-		lane_forward<NW, FULL>(acch, odd2, f2h);
-		lane_forward<NW, FULL>(accl, odd2, f2l);
-		lane_forward<NW, FULL>(accn, odd2, n2);
 		lane_reversed<NW, FULL>(acch, odd2, r2h);
 		lane_reversed<NW, FULL>(accl, odd2, r2l);
 		lane_reversed<NW, FULL>(accn, odd2, n2r);
@@ -933,8 +949,13 @@ __device__ __noinline__ uint32_t lane_tile_n(const KArgs& A, const SmemTables& T
 		}
 	}
 	int fwd = -1, rev = -1;
+	uint32_t n2[NW]; // forward N plane of read 2 (scans, trimN)
+	lane_flip<NW, FULL>(n2r, n2);
 	if (__any_sync(kFull, plain && key == kNoKey))
 	{
+		uint32_t f2h[NW], f2l[NW];
+		lane_flip<NW, FULL>(r2h, f2h);
+		lane_flip<NW, FULL>(r2l, f2l);
 		if (A.seed_ok)
 		{
 			fwd = lane_adapter_scan_seeds<NW, FULL, true>(A, T, F, f1h, f1l, n1, scr, A.a1off, A.a1h, A.a1l, A.a1n, A.a1maxmm);
@@ -1117,7 +1138,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 		}
 
 		// ---- pack both reads from the staged rows, then hand the stage back ----
-		uint32_t f1h[NW], f1l[NW], f2h[NW], f2l[NW], r2l[NW];
+		uint32_t f1h[NW], f1l[NW], r2l[NW];
 		// A parity wait is only meaningful while the barrier is at most one phase behind: claims can run further ahead of the
 		// producer than the ring is deep (8 warps, 2-4 stages), so a warp first waits until its tile's copies have been issued --
 		// from then on the stage's barrier is in this tile's phase or has just completed it.
@@ -1141,8 +1162,6 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 			lane_forward<NW, FULL>(accl, row1 & 2u, f1l);
 			lane_load_acc<NW>(copy, 1, 0, acch);
 			lane_load_acc<NW>(copy, 1, 1, accl);
-			lane_forward<NW, FULL>(acch, row2 & 2u, f2h);
-			lane_forward<NW, FULL>(accl, row2 & 2u, f2l);
 			lane_reversed<NW, FULL>(acch, row2 & 2u, r2h);
 			lane_reversed<NW, FULL>(accl, row2 & 2u, r2l);
 			plain = plain && bad == 0;
@@ -1189,7 +1208,7 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 						mml += __popc(x);
 					}
 					mmlq[q] = mml;
-					any |= mml <= lds_s16_at<64 * q>(ta); // F.thr[32q + r]
+					any |= mml <= lds_s16_const_at<64 * q>(ta); // F.thr[32q + r]
 				});
 				if (any && plain) // rare: queue the offsets for the exact count
 				{
@@ -1223,6 +1242,16 @@ __global__ void __launch_bounds__((CW + 1) * 32, MINB) trim_lanes_kernel(const _
 		int fwd = -1, rev = -1;
 		if (__any_sync(kFull, plain && key == kNoKey))
 		{
+			// read 2 in its original orientation (steps 2/3 scan it forward): the reversed planes the other way round. Formed only
+			// now -- batches in which every pair has an insert match never need them, and the sweep has that many registers more
+			uint32_t f2h[NW], f2l[NW];
+			{
+				uint32_t r2h[NW];
+#pragma unroll
+				for (int w = 0; w < NW; ++w) r2h[w] = lds_u32(copy + (2u * (NW + 1) + w) * 128u);
+				lane_flip<NW, FULL>(r2h, f2h);
+				lane_flip<NW, FULL>(r2l, f2l);
+			}
 			if (A.seed_ok)
 			{
 				fwd = lane_adapter_scan_seeds<NW, FULL>(A, T, F, f1h, f1l, f1h, copy, A.a1off, A.a1h, A.a1l, A.a1n, A.a1maxmm);
