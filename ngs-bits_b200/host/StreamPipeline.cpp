@@ -147,12 +147,17 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 		int slot;
 		std::unique_ptr<TextChunk> a, b;
 	};
+	// Chunks in flight, in submission order. This thread feeds (pairs chunks, copies them into a pinned slot, submits); a second thread
+	// retires them IN ORDER (waits for the device, adds the counters, hands the output text to the writers), so that the two host-side
+	// copies of a chunk overlap instead of adding up. `in_flight` counts submitted-and-not-yet-retired chunks (= slots in use).
 	std::deque<InFlight> in_flight;
+	std::mutex fl_mu;
+	std::condition_variable fl_cv;
+	bool fl_done = false;             // no more chunks will be submitted
+	std::exception_ptr retire_error;  // first exception of the retire thread
 	int next_slot = 0;
 
-	auto retire = [&]() {
-		InFlight f = std::move(in_flight.front());
-		in_flight.pop_front();
+	auto retire_one = [&](InFlight& f) {
 		spg_fq_output o;
 		clk::time_point t0 = clk::now();
 		if (spg_fq_wait(fq, f.slot, &o) != SPG_OK) throw Exception(spg_last_error(engine));
@@ -181,9 +186,66 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 		stats.reads_removed += (double)st.reads_removed;
 		t_stats += since(t0);
 		t0 = clk::now();
-		for (int k = 0; k < 4; ++k)
-			if (writers[k] && o.out_bytes[k] > 0) writers[k]->write(o.out[k], (size_t)o.out_bytes[k]);
+		// the two (or four) output texts are copied into the writers' pieces side by side
+		std::thread second;
+		if (writers[1] && o.out_bytes[1] > 0) second = std::thread([&]() { writers[1]->write(o.out[1], (size_t)o.out_bytes[1]); });
+		try
+		{
+			for (int k = 0; k < 4; ++k)
+				if (k != 1 && writers[k] && o.out_bytes[k] > 0) writers[k]->write(o.out[k], (size_t)o.out_bytes[k]);
+		}
+		catch (...)
+		{
+			if (second.joinable()) second.join();
+			throw;
+		}
+		if (second.joinable()) second.join();
 		t_write += since(t0);
+	};
+	std::thread retirer([&]() {
+		try
+		{
+			for (;;)
+			{
+				std::unique_lock<std::mutex> l(fl_mu);
+				fl_cv.wait(l, [&] { return !in_flight.empty() || fl_done; });
+				if (in_flight.empty()) break;
+				InFlight& f = in_flight.front(); // stays in the queue (its slot stays taken) until it is retired
+				l.unlock();
+				retire_one(f);
+				l.lock();
+				in_flight.pop_front();
+				fl_cv.notify_all();
+			}
+		}
+		catch (...)
+		{
+			std::lock_guard<std::mutex> l(fl_mu);
+			retire_error = std::current_exception();
+			fl_cv.notify_all();
+		}
+	});
+	struct RetireGuard
+	{
+		std::thread& t;
+		std::mutex& mu;
+		std::condition_variable& cv;
+		bool& done;
+		~RetireGuard()
+		{
+			{
+				std::lock_guard<std::mutex> l(mu);
+				done = true;
+			}
+			cv.notify_all();
+			if (t.joinable()) t.join();
+		}
+	} retire_guard{retirer, fl_mu, fl_cv, fl_done};
+	// blocks until at most `keep` chunks are in flight; rethrows what the retire thread ran into
+	auto drain_to = [&](size_t keep) {
+		std::unique_lock<std::mutex> l(fl_mu);
+		fl_cv.wait(l, [&] { return in_flight.size() <= keep || retire_error; });
+		if (retire_error) std::rethrow_exception(retire_error);
 	};
 
 	auto moreEntries = [&](size_t fi, bool first_has_more) {
@@ -209,7 +271,7 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 		if (a->file_index != b->file_index) throw ProgrammingException("readers out of step");
 		if (a->records != b->records)
 		{
-			while (!in_flight.empty()) retire(); // the pairs in front of the mismatch are processed like in the reference
+			drain_to(0); // the pairs in front of the mismatch are processed like in the reference
 			moreEntries(a->file_index, a->records > b->records);
 		}
 		// one file ended on this chunk, the other did not: whatever follows in the other file is a surplus entry
@@ -221,7 +283,7 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 			if (!nxt) throw ProgrammingException("reader ended inside a file");
 			if (nxt->records > 0)
 			{
-				while (!in_flight.empty()) retire();
+				drain_to(0);
 				moreEntries(a->file_index, !a->file_end);
 			}
 			open->file_end = nxt->file_end;
@@ -232,7 +294,7 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 		const int64_t need_text = (int64_t)std::max(a->data.size(), b->data.size());
 		if (!fq || need_len > fq_max_len || need_text > fq_text_cap)
 		{
-			while (!in_flight.empty()) retire();
+			drain_to(0);
 			closeStream();
 			spg_fq_config cfg;
 			memset(&cfg, 0, sizeof(cfg));
@@ -252,19 +314,32 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 			// results do not depend on it)
 			spg_set_option(engine, SPG_OPT_FULL_LEN, need_len);
 		}
-		if ((int)in_flight.size() == n_slots) retire();
+		drain_to((size_t)n_slots - 1); // a free slot (slots are used round robin and retired in order)
 		const int slot = next_slot;
 		next_slot = (next_slot + 1) % n_slots;
 		spg_fq_input in;
 		if (spg_fq_buffers(fq, slot, &in) != SPG_OK) throw Exception(spg_last_error(engine));
 		t0 = clk::now();
-		memcpy(in.text1, a->data.data(), a->data.size());
-		memcpy(in.text2, b->data.data(), b->data.size());
+		{
+			std::thread second([&]() { memcpy(in.text2, b->data.data(), b->data.size()); });
+			memcpy(in.text1, a->data.data(), a->data.size());
+			second.join();
+		}
 		t_copy += since(t0);
 		if (spg_fq_submit(fq, slot, (int64_t)a->data.size(), (int64_t)b->data.size(), 1, 1) != SPG_OK) throw Exception(spg_last_error(engine));
-		in_flight.push_back(InFlight{slot, std::move(a), std::move(b)});
+		{
+			std::lock_guard<std::mutex> l(fl_mu);
+			in_flight.push_back(InFlight{slot, std::move(a), std::move(b)});
+		}
+		fl_cv.notify_all();
 	}
-	while (!in_flight.empty()) retire();
+	drain_to(0);
+	{
+		std::lock_guard<std::mutex> l(fl_mu);
+		fl_done = true;
+	}
+	fl_cv.notify_all();
+	retirer.join();
 	closeStream();
 	if (acons_unknown) throw ArgumentException("Unknown base in the adapter consensus window!"); // Pileup::inc
 	for (int i = 0; i < 40; ++i)

@@ -140,7 +140,7 @@ def test_stats_only_stream_against_oracle(sp, single):
     batch.quals1[:] = np.minimum(batch.quals1, 74)
     batch.quals2[:] = np.minimum(batch.quals2, 74)
     n = batch.n
-    eng = sp.Engine(sp.TrimmingParameters(qc=2), devices=(0,))
+    eng = sp.Engine(sp.TrimmingParameters(qc=6), devices=(0,))  # 2: the checks of FastqEntry::validate, +4: the plot histograms
     fq = sp.FastqStream(eng, n_slots=2, max_pairs=1024, max_len=160, text_cap=4 << 20, stats_only=True, single_end=single, validate=True)
     t1, t2 = _fastq_text(batch, 1, n), (b"" if single else _fastq_text(batch, 2, n))
     off1 = off2 = 0
