@@ -21,6 +21,7 @@
 #include "spg_kernel.cuh"
 #include "spg_lanes.cuh"
 #include "spg_qc.cuh"
+#include "spg_qc_lanes.cuh"
 #include "spg_fastq.cuh"
 
 namespace
@@ -225,6 +226,7 @@ struct Device
 	Occ full_occ[4][9]; // the variants compiled for one read length (full_index)
 	Occ lane_occ[4][9]; // the lane-per-pair kernels of the same read lengths
 	Occ qc_occ[3];      // qc_kernel, NW = 5,8,10
+	Occ qc_lane_occ[3]; // qc_lanes_kernel, NW = 5,8,10
 };
 
 enum SlotState
@@ -639,6 +641,29 @@ cudaError_t launch_qc_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, Dev
 	return cudaGetLastError();
 }
 
+// the lane-per-pair form of the statistics kernel (spg_qc_lanes.cuh): one CTA of 16 consumer warps + producer per SM, ring as deep as fits
+#ifndef SPG_QC_LANE_CW
+#define SPG_QC_LANE_CW 16
+#endif
+constexpr int kQcLaneCW = SPG_QC_LANE_CW;
+template <int NW>
+cudaError_t launch_qc_lanes_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
+{
+	const size_t stage = spg::qc_lane_stage_bytes(a.stride);
+	int stages = spg::kQcLaneStagesMax;
+	while (stages > 2 && stages * stage > 196 * 1024) --stages;
+	a.stages = stages;
+	a.tile_pairs = 32;
+	const size_t smem = stages * stage;
+	int occ = 1;
+	cudaError_t e0 = resident_ctas(spg::qc_lanes_kernel<NW, kQcLaneCW>, *occ_cache, (kQcLaneCW + 1) * 32, smem, mu, occ);
+	if (e0 != cudaSuccess) return e0;
+	const long long n_tiles = (a.n_pairs + 31) / 32;
+	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * occ);
+	spg::qc_lanes_kernel<NW, kQcLaneCW><<<grid, (kQcLaneCW + 1) * 32, smem, stream>>>(a);
+	return cudaGetLastError();
+}
+
 int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, const uint8_t* b2, const uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride,
               long long n, cudaStream_t stream, const int* n_dev = nullptr, bool forward_only = false, int* bad_flag = nullptr)
 {
@@ -669,11 +694,12 @@ int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, con
 		a.bin_of_int[k] = (uint8_t)std::min(59L, std::max(0L, b));
 	}
 	cudaError_t e = cudaSuccess;
+	const bool lanes = ctx->kernel_layout != 1; // SPG_OPT_KERNEL 1 keeps the warp-per-pair form
 	switch (nw_for_qc(stride))
 	{
-		case 5: e = launch_qc_cfg<5>(a, d.sm_count, stream, &d.qc_occ[0], ctx->mu); break;
-		case 8: e = launch_qc_cfg<8>(a, d.sm_count, stream, &d.qc_occ[1], ctx->mu); break;
-		case 10: e = launch_qc_cfg<10>(a, d.sm_count, stream, &d.qc_occ[2], ctx->mu); break;
+		case 5: e = lanes ? launch_qc_lanes_cfg<5>(a, d.sm_count, stream, &d.qc_lane_occ[0], ctx->mu) : launch_qc_cfg<5>(a, d.sm_count, stream, &d.qc_occ[0], ctx->mu); break;
+		case 8: e = lanes ? launch_qc_lanes_cfg<8>(a, d.sm_count, stream, &d.qc_lane_occ[1], ctx->mu) : launch_qc_cfg<8>(a, d.sm_count, stream, &d.qc_occ[1], ctx->mu); break;
+		case 10: e = lanes ? launch_qc_lanes_cfg<10>(a, d.sm_count, stream, &d.qc_lane_occ[2], ctx->mu) : launch_qc_cfg<10>(a, d.sm_count, stream, &d.qc_occ[2], ctx->mu); break;
 		default:
 		{
 			const long long warps_wanted = std::min<long long>((n + 7) / 8, (long long)d.sm_count * 32); // >= 8 pairs per warp, at most 4 CTAs of 8 warps per SM

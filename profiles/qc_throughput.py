@@ -27,7 +27,9 @@ for b in range(2):  # 2 x 2.4 GB at the defaults: larger than L2, alternated bet
     l2 = torch.empty(n, dtype=torch.int16, device=dev)
     sp.synth_device(cfg, b * n, n, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
     bufs.append((t, l1, l2))
-eng = sp.Engine(sp.TrimmingParameters(qc=True), devices=(0,))
+eng = sp.Engine(sp.TrimmingParameters(qc=int(os.environ.get("SPG_QC_FLAGS", "1"))), devices=(0,))
+if os.environ.get("SPG_QC_WARP"):  # the warp-per-pair form of the kernel (round 1)
+    eng.set_option(sp.OPT_KERNEL, sp.KERNEL_WARP_PER_PAIR)
 
 
 def run(i):
@@ -48,5 +50,5 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 st = eng.qc_stats()
 assert st["reads_forward"] == (reps + 3) * n and st["errors"] == 0
-print(json.dumps({"kernel": "qc_kernel", "pairs": n, "read_len": L, "ms_per_launch": round(ms, 4), "Mpairs_per_s": round(n / ms / 1e3, 1),
+print(json.dumps({"kernel": "qc_kernel (warp per pair)" if os.environ.get("SPG_QC_WARP") else "qc_lanes_kernel", "qc_flags": int(os.environ.get("SPG_QC_FLAGS", "1")), "pairs": n, "read_len": L, "ms_per_launch": round(ms, 4), "Mpairs_per_s": round(n / ms / 1e3, 1),
                   "GB_per_s": round(n * (4 * L + 4) / ms / 1e6, 1)}))
