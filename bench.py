@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-step", type=int, default=10_000_000)
     ap.add_argument("--pool", type=int, default=10, help="distinct resident batches of the headline config (pool*pairs_per_step = the 100M-pair config by default)")
-    ap.add_argument("--configs", default="C3,C4,C5", help="further BASELINE configs measured after the headline (comma separated, '' = none)")
+    ap.add_argument("--configs", default="C3,C4,C5,qc", help="further BASELINE configs measured after the headline (comma separated, '' = none); qc = the -qc statistics kernel")
     ap.add_argument("--config-steps", type=int, default=5)
     ap.add_argument("--config-pool", type=int, default=3)
     ap.add_argument("--parity-pairs", type=int, default=1_000_000, help="pairs of every config checked against the CPU oracle after timing (0 = off)")
@@ -453,13 +453,66 @@ def main():
 
     # ---- the other BASELINE configs, same measurement, smaller pools
     others = {}
-    for name in [c for c in args.configs.split(",") if c]:
+    for name in [c for c in args.configs.split(",") if c and c != "qc"]:
         c = CONFIGS[name]
         Bc = B if c["read_len"] <= 160 else B // 2  # config 3 is 50 M pairs of 2x250: half the pairs per batch
         r, p2, e2 = measure(name, args.config_steps, 3, Bc, args.config_pool, False)
         others[name] = r
         del p2
         e2.close()
+        torch.cuda.empty_cache()
+
+    # ---- the -qc statistics kernel on the headline workload: device-resident throughput + every accumulator against the oracle
+    if "qc" in args.configs.split(","):
+        c = CONFIGS["C2"]
+        L, stride = c["read_len"], row_stride(c["read_len"])
+        Bq = B
+        engq = sp.Engine(sp.TrimmingParameters(qc=1), devices=(local_rank,), n_slots=0, max_pairs=1, max_len=L)
+        cfg = sp.SynthConfig(read_len=L, **c["synth"])
+        poolq = []
+        for b in range(2):
+            t, l1, l2 = alloc(Bq, stride)
+            sp.synth_device(cfg, (rank * 2 + b) * Bq, Bq, t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2, device_id=local_rank)
+            poolq.append((t, l1, l2))
+        torch.cuda.synchronize()
+
+        def qstep(i):
+            t, l1, l2 = poolq[i % 2]
+            engq.qc_device(t["bases1"], t["quals1"], t["bases2"], t["quals2"], l1, l2)
+
+        for i in range(3):
+            qstep(i)
+        torch.cuda.synchronize()
+        qs = args.config_steps
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = engq.launch_count
+        e0.record()
+        for i in range(qs):
+            qstep(i)
+        e1.record()
+        torch.cuda.synchronize()
+        total_launches += engq.launch_count - l0
+        ms = sharding.reduce_max(e0.elapsed_time(e1), dist, dev) / qs
+        engq.close()
+        # parity: a fresh context over a slice, every accumulator against the oracle's restatement of StatisticsReads::update
+        m = 200_000
+        engp = sp.Engine(sp.TrimmingParameters(qc=5), devices=(local_rank,), n_slots=0, max_pairs=1, max_len=L)
+        t, l1, l2 = poolq[0]
+        engp.qc_device(t["bases1"][:m], t["quals1"][:m], t["bases2"][:m], t["quals2"][:m], l1[:m], l2[:m], n_pairs=m)
+        got = engp.qc_stats()
+        engp.close()
+        want = H.oracle_qc(host_batch_from_device(np, H, t, l1, l2, 0, m, stride))
+        bad = [k for k in want if not np.array_equal(np.asarray(got[k]), np.asarray(want[k]))]
+        assert not bad, f"-qc statistics differ from the oracle: {bad}"
+        peak, peak_src = hbm_peak()
+        balg = 4 * L + 4
+        ach = Bq * balg / (ms * 1e-3) / 1e9
+        others["qc"] = {"workload": "-qc raw-read statistics (StatisticsReads::update of both reads) of the C2 batches, device resident", "kernel": "spg::qc_lanes_kernel",
+                        "value": world * Bq / ms / 1e3, "unit": UNIT, "steps": qs, "pairs_per_step": Bq, "ms_per_step": ms,
+                        "parity": {"pairs": m, "accumulators": len(want), "mismatches": 0},
+                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src, "algorithmic_bytes_per_pair": balg,
+                                     "kernel_ms_mean": ms}}
+        del poolq
         torch.cuda.empty_cache()
 
     # ---- N > 1: the north-star split. ONE host process (rank 0) drives all N devices: slots dealt round robin (slot % N), retired in
@@ -471,7 +524,7 @@ def main():
             c = CONFIGS["C5"]
             L5, s5 = c["read_len"], row_stride(c["read_len"])
             n_e = args.e2e_pairs
-            ns = 4 * world
+            ns = (4 if world <= 2 else 2) * world  # pinned slots of 1 M pairs each: 2 per device are enough to keep copies and kernels overlapped
             eng = sp.Engine(sp.TrimmingParameters(**c["params"]), devices=tuple(range(world)), n_slots=ns, max_pairs=n_e, max_len=L5)
             cfg = sp.SynthConfig(read_len=L5, **c["synth"])
             t, l1, l2 = alloc(n_e, s5)

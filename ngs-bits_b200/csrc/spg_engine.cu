@@ -642,10 +642,12 @@ cudaError_t launch_qc_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, Dev
 }
 
 // the lane-per-pair form of the statistics kernel (spg_qc_lanes.cuh): one CTA of 16 consumer warps + producer per SM, ring as deep as fits
-#ifndef SPG_QC_LANE_CW
-#define SPG_QC_LANE_CW 16
-#endif
-constexpr int kQcLaneCW = SPG_QC_LANE_CW;
+// consumer warps: every warp reads its stage during a whole pass, so the ring (196 KB / stage) bounds how many can be busy
+template <int NW>
+struct QcLaneCfg
+{
+	static constexpr int CW = NW <= 5 ? 20 : 16;
+};
 template <int NW>
 cudaError_t launch_qc_lanes_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
 {
@@ -656,11 +658,12 @@ cudaError_t launch_qc_lanes_cfg(spg::QcArgs& a, int sm_count, cudaStream_t strea
 	a.tile_pairs = 32;
 	const size_t smem = stages * stage;
 	int occ = 1;
-	cudaError_t e0 = resident_ctas(spg::qc_lanes_kernel<NW, kQcLaneCW>, *occ_cache, (kQcLaneCW + 1) * 32, smem, mu, occ);
+	constexpr int CW = QcLaneCfg<NW>::CW;
+	cudaError_t e0 = resident_ctas(spg::qc_lanes_kernel<NW, CW>, *occ_cache, (CW + 1) * 32, smem, mu, occ);
 	if (e0 != cudaSuccess) return e0;
 	const long long n_tiles = (a.n_pairs + 31) / 32;
 	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * occ);
-	spg::qc_lanes_kernel<NW, kQcLaneCW><<<grid, (kQcLaneCW + 1) * 32, smem, stream>>>(a);
+	spg::qc_lanes_kernel<NW, CW><<<grid, (CW + 1) * 32, smem, stream>>>(a);
 	return cudaGetLastError();
 }
 
