@@ -641,30 +641,32 @@ cudaError_t launch_qc_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, Dev
 	return cudaGetLastError();
 }
 
-// the lane-per-pair form of the statistics kernel (spg_qc_lanes.cuh): one CTA of 16 consumer warps + producer per SM, ring as deep as fits
-// consumer warps: every warp reads its stage during a whole pass, so the ring (196 KB / stage) bounds how many can be busy
-template <int NW>
-struct QcLaneCfg
-{
-	static constexpr int CW = NW <= 5 ? 20 : 16;
-};
-template <int NW>
-cudaError_t launch_qc_lanes_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
+// the lane-per-pair form of the statistics kernel (spg_qc_lanes.cuh): one CTA of 16-24 consumer warps + producer per SM, ring as deep as
+// fits (a stage is one plane of one read of 32 pairs; every warp holds its stage during a whole pass, the rest of the ring is prefetch)
+template <int NW, int CW>
+cudaError_t launch_qc_lanes_cw(spg::QcArgs& a, int sm_count, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
 {
 	const size_t stage = spg::qc_lane_stage_bytes(a.stride);
 	int stages = spg::kQcLaneStagesMax;
-	while (stages > 2 && stages * stage > 196 * 1024) --stages;
+	while (stages > 2 && stages * stage > 208 * 1024) --stages;
 	a.stages = stages;
 	a.tile_pairs = 32;
 	const size_t smem = stages * stage;
 	int occ = 1;
-	constexpr int CW = QcLaneCfg<NW>::CW;
 	cudaError_t e0 = resident_ctas(spg::qc_lanes_kernel<NW, CW>, *occ_cache, (CW + 1) * 32, smem, mu, occ);
 	if (e0 != cudaSuccess) return e0;
 	const long long n_tiles = (a.n_pairs + 31) / 32;
 	const int grid = (int)std::min<long long>(n_tiles, (long long)sm_count * occ);
 	spg::qc_lanes_kernel<NW, CW><<<grid, (CW + 1) * 32, smem, stream>>>(a);
 	return cudaGetLastError();
+}
+template <int NW>
+cudaError_t launch_qc_lanes_cfg(spg::QcArgs& a, int sm_count, cudaStream_t stream, Device::Occ* occ_cache, std::mutex& mu)
+{
+	// consumer warps (measured, profiles/qc_sweep_r2.txt): 24 for rows of up to 256 bytes; wider rows leave room for 20 stages only, and every
+	// warp holds one during its pass
+	if constexpr (NW <= 8) return launch_qc_lanes_cw<NW, 24>(a, sm_count, stream, occ_cache, mu);
+	else return launch_qc_lanes_cw<NW, 16>(a, sm_count, stream, occ_cache, mu);
 }
 
 int launch_qc(spg_ctx* ctx, Device& d, const uint8_t* b1, const uint8_t* q1, const uint8_t* b2, const uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride,

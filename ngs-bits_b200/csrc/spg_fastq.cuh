@@ -39,7 +39,7 @@ enum : uint8_t
 	FQ_BAD_HEADER2 = 5      // validate: header2 does not start with '+'
 };
 
-struct FqRec // where the two header lines of a record are in the text
+struct __align__(16) FqRec // where the two header lines of a record are in the text
 {
 	uint32_t hs, hl;   // start offset and length (without line ending) of the header line
 	uint32_t h2s, h2l; // same for header2
@@ -275,8 +275,100 @@ struct FqLine
 {
 	uint32_t s, e; // [s, e) without line ending
 };
-// line k of text f: from the end of line k-1 to its own end, trailing '\r' chopped; lines beyond the last one are empty
-__device__ __forceinline__ FqLine fq_line(const FqArgs& A, int f, long long k, int lines)
+
+// Copies of the row / text segments of a pair, warp-cooperative, in two phases: first every load of the pair is issued, then the
+// stores follow, so a pair costs one trip to memory (the byte-wise loop of round 1 waited for memory once per 32 bytes of each segment:
+// the two copy kernels were bound by that chain of latencies at full occupancy).
+//
+// FqTwo: two segments of the same length n (the bases and the qualities of a read). Four bytes at a time: lane w forms the w-th aligned
+// destination word from the two aligned source words that hold its bytes (funnel shift; the second one comes from the neighbouring
+// lane); two words per lane in flight cover reads of up to 256 bases, longer ones finish in a plain loop. The up to three bytes in front
+// of and behind the words go one per lane (lanes 0-2, 4-6). A source word is only read if it holds a byte of the segment, and all
+// buffers are multiples of 16 bytes, so nothing outside them is touched.
+struct FqTwo
+{
+	uint32_t nw[2], sh[2], ei[2], eb[2], lo0[2], lo1[2], ex[2];
+	const uint32_t* lp[2]; // aligned source word of this lane
+	uint32_t* sp[2];       // destination word of this lane
+};
+__device__ __forceinline__ void fq_two_load(FqTwo& T, uint8_t* d0, const uint8_t* s0, uint8_t* d1, const uint8_t* s1, uint32_t n, int lane)
+{
+#pragma unroll
+	for (int k = 0; k < 2; ++k)
+	{
+		uint8_t* dst = k ? d1 : d0;
+		const uint8_t* src = k ? s1 : s0;
+		const uint32_t head = min(n, (0u - (uint32_t)(uintptr_t)dst) & 3u);
+		const uint32_t nw = (n - head) >> 2;
+		const uint32_t mis = ((uint32_t)(uintptr_t)src + head) & 3u;
+		const uint32_t nld = nw + (mis ? 1u : 0u); // source words that hold bytes of the destination words
+		T.nw[k] = nw;
+		T.sh[k] = 8u * mis;
+		T.lp[k] = reinterpret_cast<const uint32_t*>(src + (int)(head - mis)) + lane;
+		T.sp[k] = reinterpret_cast<uint32_t*>(dst + head) + lane;
+		const uint32_t done = head + 4u * nw, t = (uint32_t)lane - 4u;
+		T.ei[k] = (uint32_t)lane < head ? (uint32_t)lane : (t < n - done ? done + t : 0xFFFFFFFFu);
+		T.eb[k] = T.lo0[k] = T.lo1[k] = T.ex[k] = 0;
+		if (T.ei[k] != 0xFFFFFFFFu) T.eb[k] = src[T.ei[k]];
+		if ((uint32_t)lane < nld) T.lo0[k] = T.lp[k][0];
+		if ((uint32_t)lane + 32u < nld) T.lo1[k] = T.lp[k][32];
+		if (lane == 31 && 64u < nld) T.ex[k] = T.lp[k][33];
+	}
+}
+__device__ __forceinline__ void fq_two_store(const FqTwo& T, uint8_t* d0, const uint8_t* s0, uint8_t* d1, const uint8_t* s1, int lane)
+{
+#pragma unroll
+	for (int k = 0; k < 2; ++k)
+	{
+		const uint32_t n0 = __shfl_down_sync(0xffffffffu, T.lo0[k], 1), n1 = __shfl_down_sync(0xffffffffu, T.lo1[k], 1);
+		const uint32_t first1 = __shfl_sync(0xffffffffu, T.lo1[k], 0);
+		const uint32_t hi0 = lane == 31 ? first1 : n0, hi1 = lane == 31 ? T.ex[k] : n1;
+		if ((uint32_t)lane < T.nw[k]) T.sp[k][0] = __funnelshift_r(T.lo0[k], hi0, T.sh[k]);
+		if ((uint32_t)lane + 32u < T.nw[k]) T.sp[k][32] = __funnelshift_r(T.lo1[k], hi1, T.sh[k]);
+		if (T.ei[k] != 0xFFFFFFFFu) (k ? d1 : d0)[T.ei[k]] = (uint8_t)T.eb[k];
+		for (uint32_t w = 64u + (uint32_t)lane; w < T.nw[k]; w += 32u) // reads of more than 256 bases
+		{
+			const uint32_t lo = T.lp[k][w - (uint32_t)lane], hi = T.sh[k] ? T.lp[k][w - (uint32_t)lane + 1u] : 0u;
+			T.sp[k][w - (uint32_t)lane] = __funnelshift_r(lo, hi, T.sh[k]);
+		}
+	}
+}
+
+// FqText: a short segment (a header line) byte-wise: the first 64 bytes in flight, longer ones finish in a plain loop
+struct FqText
+{
+	uint32_t b0, b1;
+};
+__device__ __forceinline__ void fq_text_load(FqText& T, const uint8_t* src, uint32_t n, int lane)
+{
+	T.b0 = T.b1 = 0;
+	if ((uint32_t)lane < n) T.b0 = src[lane];
+	if ((uint32_t)lane + 32u < n) T.b1 = src[lane + 32];
+}
+__device__ __forceinline__ void fq_text_store(const FqText& T, uint8_t* dst, const uint8_t* src, uint32_t n, int lane)
+{
+	if ((uint32_t)lane < n) dst[lane] = (uint8_t)T.b0;
+	if ((uint32_t)lane + 32u < n) dst[lane + 32] = (uint8_t)T.b1;
+	for (uint32_t i = 64u + (uint32_t)lane; i < n; i += 32u) dst[i] = src[i];
+}
+
+// first ' ' of a line (or its length), warp-cooperative; `c0` is this lane's byte of the first 32 (0x100 beyond the line)
+__device__ __forceinline__ uint32_t fq_token_len(const uint8_t* t, FqLine L, uint32_t c0, int lane)
+{
+	const uint32_t len = L.e - L.s;
+	for (uint32_t base = 0; base < len; base += 32)
+	{
+		const uint32_t i = base + (uint32_t)lane;
+		const uint32_t c = base == 0 ? c0 : (i < len ? (uint32_t)t[L.s + i] : 0x100u);
+		const uint32_t m = __ballot_sync(0xffffffffu, c == (uint32_t)' ');
+		if (m) return base + (uint32_t)(__ffs((int)m) - 1);
+	}
+	return len;
+}
+
+// bounds of line k of text f as readLine delivers it: from the end of the line before to its own end, trailing '\r' chopped; lines beyond
+// the last one are empty. `a`, `b` = nl[k-1], nl[k] (loaded by the caller).
+__device__ __forceinline__ FqLine fq_line_of(const FqArgs& A, int f, long long k, int lines, uint32_t a, uint32_t b)
 {
 	FqLine L;
 	if (k >= lines)
@@ -284,41 +376,73 @@ __device__ __forceinline__ FqLine fq_line(const FqArgs& A, int f, long long k, i
 		L.s = L.e = A.bytes[f];
 		return L;
 	}
-	const uint32_t* nl = A.nl[f];
-	L.s = k == 0 ? 0u : nl[k - 1] + 1u;
-	L.e = nl[k];
+	L.s = k == 0 ? 0u : a + 1u;
+	L.e = b;
 	const uint8_t* t = A.text[f];
 	while (L.e > L.s && t[L.e - 1] == '\r') --L.e;
 	return L;
 }
 
-// first ' ' of a line (or its length): warp-cooperative
-__device__ __forceinline__ uint32_t fq_token_len(const uint8_t* t, FqLine L, int lane)
-{
-	const uint32_t len = L.e - L.s;
-	for (uint32_t base = 0; base < len; base += 32)
-	{
-		const uint32_t i = base + (uint32_t)lane;
-		const uint32_t m = __ballot_sync(0xffffffffu, i < len && t[L.s + i] == ' ');
-		if (m) return base + (uint32_t)(__ffs((int)m) - 1);
-	}
-	return len;
-}
-
-// one warp per pair: rows, lengths, header locations, header check
-__global__ void __launch_bounds__(256) fq_pack(const __grid_constant__ FqArgs A)
+// one warp per pair: rows, lengths, header locations, header check. Three trips to memory per pair: the line index (lanes 0-7 load the
+// entries of the eight lines, one pair ahead), the bytes in front of the line ends + the first 32 bytes of the two headers, then all
+// four rows at once.
+__global__ void __launch_bounds__(256, 3) fq_pack(const __grid_constant__ FqArgs A)
 {
 	const int lane = threadIdx.x & 31;
 	const long long gwarp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
 	const int n = A.plan->n_pairs;
+	const int nfiles = A.single_end ? 1 : 2;
+	const int lf = (lane >> 2) & 1, li = lane & 3; // text and line of the record this lane looks up (lanes 0-7)
+	const int my_lines = A.plan->lines[lf];
+	const bool looks_up = lane < 4 * nfiles;
 	int max_len = 0;
+	uint32_t na = 0, nb = 0; // nl[k-1], nl[k] of this lane's line of the current pair
+	auto load_index = [&](long long p) {
+		const long long k = 4 * p + li;
+		na = nb = 0;
+		if (looks_up && k < my_lines)
+		{
+			if (k > 0) na = A.nl[lf][k - 1];
+			nb = A.nl[lf][k];
+		}
+	};
+	if (gwarp < n) load_index(gwarp);
 	for (long long p = gwarp; p < n; p += nwarps)
 	{
-		uint8_t st = FQ_OK;
-		FqLine hdr[2];
+		const uint32_t ca = na, cb = nb;
+		if (p + nwarps < n) load_index(p + nwarps);
+		// the first 32 bytes behind the start of each header line (masked with the line's length below): issued together with the '\r' checks
+		uint32_t hc[2] = {0x100u, 0x100u};
+#pragma unroll
 		for (int f = 0; f < 2; ++f)
 		{
+			const long long k0 = 4 * p;
+			const uint32_t a0 = __shfl_sync(0xffffffffu, ca, 4 * f);
+			const uint32_t hstart = k0 >= A.plan->lines[f] ? A.bytes[f] : (k0 == 0 ? 0u : a0 + 1u);
+			if (f < nfiles && hstart + (uint32_t)lane < A.bytes[f]) hc[f] = A.text[f][hstart + (uint32_t)lane];
+		}
+		FqLine mine;
+		mine.s = mine.e = 0;
+		if (looks_up) mine = fq_line_of(A, lf, 4 * p + li, my_lines, ca, cb);
+		FqLine ln[2][4];
+#pragma unroll
+		for (int f = 0; f < 2; ++f)
+#pragma unroll
+			for (int i = 0; i < 4; ++i)
+			{
+				ln[f][i].s = __shfl_sync(0xffffffffu, mine.s, 4 * f + i);
+				ln[f][i].e = __shfl_sync(0xffffffffu, mine.e, 4 * f + i);
+			}
+		uint8_t st = FQ_OK;
+		FqTwo two[2];
+		uint8_t* rdst[2][2];
+		const uint8_t* rsrc[2][2];
+#pragma unroll
+		for (int f = 0; f < 2; ++f)
+		{
+			rdst[f][0] = rdst[f][1] = nullptr;
+			rsrc[f][0] = rsrc[f][1] = nullptr;
 			if (f == 1 && A.single_end) // no mate: an empty read 2
 			{
 				if (lane == 0)
@@ -330,51 +454,57 @@ __global__ void __launch_bounds__(256) fq_pack(const __grid_constant__ FqArgs A)
 				}
 				continue;
 			}
-			const int lines = A.plan->lines[f];
 			const uint8_t* t = A.text[f];
-			hdr[f] = fq_line(A, f, 4 * p, lines);
-			const FqLine b = fq_line(A, f, 4 * p + 1, lines);
-			const FqLine h2 = fq_line(A, f, 4 * p + 2, lines);
-			const FqLine q = fq_line(A, f, 4 * p + 3, lines);
+			const FqLine hdr = ln[f][0], b = ln[f][1], h2 = ln[f][2], q = ln[f][3];
 			const uint32_t lb = b.e - b.s, lq = q.e - q.s;
 			max_len = max(max_len, (int)min(max(lb, lq), 0x7fffffffu));
 			uint32_t len = lb;
 			if (A.validate && st == FQ_OK) // FastqEntry::validate, in its order (FastqFileStream.cpp:7-18)
 			{
-				if (hdr[f].e == hdr[f].s || t[hdr[f].s] != '@') st = FQ_BAD_HEADER;
+				if (hdr.e == hdr.s || t[hdr.s] != '@') st = FQ_BAD_HEADER;
 				else if (h2.e == h2.s || t[h2.s] != '+') st = FQ_BAD_HEADER2;
 			}
 			if (lb != lq && st == FQ_OK) st = FQ_LENGTH_MISMATCH;
 			if ((lb > (uint32_t)A.stride || lq > (uint32_t)A.stride || lb >= (uint32_t)SPG_MAXLEN) && st == FQ_OK) st = FQ_TOO_LONG;
 			if (lb > (uint32_t)A.stride || lq > (uint32_t)A.stride || lb >= (uint32_t)SPG_MAXLEN || lb != lq) len = 0; // keeps the kernels behind inside the rows
-			uint8_t* rb = A.rows[2 * f] + (size_t)p * A.stride;
-			uint8_t* rq = A.rows[2 * f + 1] + (size_t)p * A.stride;
-			for (uint32_t i = lane; i < len; i += 32)
-			{
-				rb[i] = t[b.s + i];
-				rq[i] = t[q.s + i];
-			}
+			rdst[f][0] = A.rows[2 * f] + (size_t)p * A.stride;
+			rdst[f][1] = A.rows[2 * f + 1] + (size_t)p * A.stride;
+			rsrc[f][0] = t + b.s;
+			rsrc[f][1] = t + q.s;
+			fq_two_load(two[f], rdst[f][0], rsrc[f][0], rdst[f][1], rsrc[f][1], len, lane);
 			if (lane == 0)
 			{
 				A.len[f][p] = (uint16_t)len;
 				FqRec r;
-				r.hs = hdr[f].s;
-				r.hl = hdr[f].e - hdr[f].s;
+				r.hs = hdr.s;
+				r.hl = hdr.e - hdr.s;
 				r.h2s = h2.s;
 				r.h2l = h2.e - h2.s;
 				A.rec[f][p] = r;
 			}
 		}
+		fq_two_store(two[0], rdst[0][0], rsrc[0][0], rdst[0][1], rsrc[0][1], lane);
+		if (!A.single_end) fq_two_store(two[1], rdst[1][0], rsrc[1][0], rdst[1][1], rsrc[1][1], lane);
 		// headers must match up to the first space, "/1" and "/2" aside (AnalysisWorker.cpp:110-120); ReadQC does not compare them
 		if (!A.single_end && !A.validate)
 		{
 			const uint8_t* t1 = A.text[0];
 			const uint8_t* t2 = A.text[1];
-			uint32_t n1 = fq_token_len(t1, hdr[0], lane), n2 = fq_token_len(t2, hdr[1], lane);
-			if (n1 >= 2 && n2 >= 2 && t1[hdr[0].s + n1 - 2] == '/' && t1[hdr[0].s + n1 - 1] == '1' && t2[hdr[1].s + n2 - 2] == '/' && t2[hdr[1].s + n2 - 1] == '2')
+			const FqLine h1 = ln[0][0], h2 = ln[1][0];
+			const uint32_t c1 = (uint32_t)lane < h1.e - h1.s ? hc[0] : 0x100u, c2 = (uint32_t)lane < h2.e - h2.s ? hc[1] : 0x100u;
+			uint32_t n1 = fq_token_len(t1, h1, c1, lane), n2 = fq_token_len(t2, h2, c2, lane);
+			if (n1 >= 2 && n2 >= 2)
 			{
-				n1 -= 2;
-				n2 -= 2;
+				// the last two bytes of both tokens: from the preloaded bytes where they are among the first 32
+				auto hb = [&](const uint8_t* t, FqLine L, uint32_t c0, uint32_t idx) -> uint32_t {
+					return idx < 32u ? __shfl_sync(0xffffffffu, c0, (int)idx) : (uint32_t)t[L.s + idx];
+				};
+				const uint32_t e1 = hb(t1, h1, c1, n1 - 2), e2 = hb(t1, h1, c1, n1 - 1), e3 = hb(t2, h2, c2, n2 - 2), e4 = hb(t2, h2, c2, n2 - 1);
+				if (e1 == '/' && e2 == '1' && e3 == '/' && e4 == '2')
+				{
+					n1 -= 2;
+					n2 -= 2;
+				}
 			}
 			bool diff = n1 != n2;
 			if (!diff)
@@ -382,7 +512,9 @@ __global__ void __launch_bounds__(256) fq_pack(const __grid_constant__ FqArgs A)
 				for (uint32_t base = 0; base < n1 && !diff; base += 32)
 				{
 					const uint32_t i = base + (uint32_t)lane;
-					diff = __any_sync(0xffffffffu, i < n1 && t1[hdr[0].s + i] != t2[hdr[1].s + i]);
+					const uint32_t x1 = base == 0 ? c1 : (uint32_t)(i < n1 ? t1[h1.s + i] : 0);
+					const uint32_t x2 = base == 0 ? c2 : (uint32_t)(i < n1 ? t2[h2.s + i] : 0);
+					diff = __any_sync(0xffffffffu, i < n1 && x1 != x2);
 				}
 			}
 			if (diff) st = FQ_HEADER_MISMATCH; // the first check of the worker: wins over the length checks
@@ -574,28 +706,27 @@ __global__ void __launch_bounds__(1024) fq_out_scan(const __grid_constant__ FqAr
 	}
 }
 
-// copies `n` bytes warp-cooperatively
-__device__ __forceinline__ void fq_copy(uint8_t* dst, const uint8_t* src, uint32_t n, int lane)
+// one record "header\nbases\nheader2\nquals\n" at dst, in the two phases of FqTwo / FqText; lanes 28-31 write the four line ends
+struct FqRecord
 {
-	for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+	FqText h, h2;
+	FqTwo rows;
+};
+__device__ __forceinline__ void fq_record_load(FqRecord& R, uint8_t* dst, const uint8_t* text, FqRec r, const uint8_t* bases, const uint8_t* quals, uint32_t len, int lane)
+{
+	fq_text_load(R.h, text + r.hs, r.hl, lane);
+	fq_text_load(R.h2, text + r.h2s, r.h2l, lane);
+	fq_two_load(R.rows, dst + r.hl + 1u, bases, dst + r.hl + len + r.h2l + 3u, quals, len, lane);
 }
-
-// one record "header\nbases\nheader2\nquals\n" at dst
-__device__ __forceinline__ void fq_write_record(uint8_t* dst, const uint8_t* text, FqRec r, const uint8_t* bases, const uint8_t* quals, uint32_t len, int lane)
+__device__ __forceinline__ void fq_record_store(const FqRecord& R, uint8_t* dst, const uint8_t* text, FqRec r, const uint8_t* bases, const uint8_t* quals, uint32_t len, int lane)
 {
-	fq_copy(dst, text + r.hs, r.hl, lane);
-	dst += r.hl;
-	fq_copy(dst + 1, bases, len, lane);
-	uint8_t* d2 = dst + 1 + len;
-	fq_copy(d2 + 1, text + r.h2s, r.h2l, lane);
-	uint8_t* d3 = d2 + 1 + r.h2l;
-	fq_copy(d3 + 1, quals, len, lane);
-	if (lane == 0)
+	fq_text_store(R.h, dst, text + r.hs, r.hl, lane);
+	fq_text_store(R.h2, dst + r.hl + len + 2u, text + r.h2s, r.h2l, lane);
+	fq_two_store(R.rows, dst + r.hl + 1u, bases, dst + r.hl + len + r.h2l + 3u, quals, lane);
+	if (lane >= 28)
 	{
-		dst[0] = '\n';
-		d2[0] = '\n';
-		d3[0] = '\n';
-		d3[1 + len] = '\n';
+		const uint32_t at = lane == 28 ? r.hl : lane == 29 ? r.hl + len + 1u : lane == 30 ? r.hl + len + r.h2l + 2u : r.hl + 2u * len + r.h2l + 3u;
+		dst[at] = '\n';
 	}
 }
 
@@ -613,7 +744,7 @@ __device__ __forceinline__ int fq_base_index(uint8_t c) // Pileup::inc (src/cppN
 	}
 }
 
-__global__ void __launch_bounds__(kFqOutPairs) fq_out_write(const __grid_constant__ FqArgs A)
+__global__ void __launch_bounds__(kFqOutPairs, 2) fq_out_write(const __grid_constant__ FqArgs A)
 {
 	const int n = A.plan->n_pairs;
 	const int first = blockIdx.x * kFqOutPairs;
@@ -631,12 +762,35 @@ __global__ void __launch_bounds__(kFqOutPairs) fq_out_write(const __grid_constan
 		for (int k = 0; k < 4; ++k) offs[k][threadIdx.x] = A.out_block[k][blockIdx.x] + sz[k];
 	}
 	__syncthreads();
+	// a warp writes 32 consecutive pairs (neighbouring rows share sectors); the result record and the header locations of a pair are
+	// loaded one pair ahead, the loads of its two records are issued before the first store (fq_record_load / fq_record_store)
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	for (int j = warp; j < kFqOutPairs; j += kFqOutPairs / 32)
+	const int j0 = warp * 32;
+	spg_result r_nx;
+	FqRec a_nx, b_nx;
+	r_nx.len1 = r_nx.len2 = 0;
+	r_nx.best_offset = -1;
+	r_nx.flags = r_nx.status = 0;
+	a_nx.hs = a_nx.hl = a_nx.h2s = a_nx.h2l = 0;
+	b_nx = a_nx;
+	if (first + j0 < n)
 	{
-		const int p = first + j;
+		r_nx = A.res[first + j0];
+		a_nx = A.rec[0][first + j0];
+		b_nx = A.rec[1][first + j0];
+	}
+	for (int jj = 0; jj < 32; ++jj)
+	{
+		const int j = j0 + jj, p = first + j;
 		if (p >= n) break;
-		const spg_result r = A.res[p];
+		const spg_result r = r_nx;
+		const FqRec ra = a_nx, rb = b_nx;
+		if (jj + 1 < 32 && p + 1 < n)
+		{
+			r_nx = A.res[p + 1];
+			a_nx = A.rec[0][p + 1];
+			b_nx = A.rec[1][p + 1];
+		}
 		const int l1 = r.len1, l2 = r.len2;
 		const bool ok1 = l1 >= A.min_len, ok2 = l2 >= A.min_len;
 		const uint8_t* b1 = A.rows[0] + (size_t)p * A.stride;
@@ -645,16 +799,37 @@ __global__ void __launch_bounds__(kFqOutPairs) fq_out_write(const __grid_constan
 		const uint8_t* q2 = A.rows[3] + (size_t)p * A.stride;
 		if (A.fixed_trim)
 		{
-			if (!(r.flags & SPG_F_DROPPED)) fq_write_record(A.out[0] + offs[0][j], A.text[0], A.rec[0][p], b1 + r.best_offset, q1 + r.best_offset, (uint32_t)l1, lane);
+			if (!(r.flags & SPG_F_DROPPED))
+			{
+				FqRecord R;
+				uint8_t* d = A.out[0] + offs[0][j];
+				fq_record_load(R, d, A.text[0], ra, b1 + r.best_offset, q1 + r.best_offset, (uint32_t)l1, lane);
+				fq_record_store(R, d, A.text[0], ra, b1 + r.best_offset, q1 + r.best_offset, (uint32_t)l1, lane);
+			}
 			continue;
 		}
 		if (ok1 && ok2)
 		{
-			fq_write_record(A.out[0] + offs[0][j], A.text[0], A.rec[0][p], b1, q1, (uint32_t)l1, lane);
-			fq_write_record(A.out[1] + offs[1][j], A.text[1], A.rec[1][p], b2, q2, (uint32_t)l2, lane);
+			FqRecord R1, R2;
+			uint8_t* d1 = A.out[0] + offs[0][j];
+			uint8_t* d2 = A.out[1] + offs[1][j];
+			fq_record_load(R1, d1, A.text[0], ra, b1, q1, (uint32_t)l1, lane);
+			fq_record_load(R2, d2, A.text[1], rb, b2, q2, (uint32_t)l2, lane);
+			fq_record_store(R1, d1, A.text[0], ra, b1, q1, (uint32_t)l1, lane);
+			fq_record_store(R2, d2, A.text[1], rb, b2, q2, (uint32_t)l2, lane);
 		}
-		else if (A.singles && ok1) fq_write_record(A.out[2] + offs[2][j], A.text[0], A.rec[0][p], b1, q1, (uint32_t)l1, lane);
-		else if (A.singles && ok2) fq_write_record(A.out[3] + offs[3][j], A.text[1], A.rec[1][p], b2, q2, (uint32_t)l2, lane);
+		else if (A.singles && (ok1 || ok2))
+		{
+			FqRecord R;
+			uint8_t* d = ok1 ? A.out[2] + offs[2][j] : A.out[3] + offs[3][j];
+			const uint8_t* text = ok1 ? A.text[0] : A.text[1];
+			const FqRec rr = ok1 ? ra : rb;
+			const uint8_t* bb = ok1 ? b1 : b2;
+			const uint8_t* qq = ok1 ? q1 : q2;
+			const uint32_t ll = (uint32_t)(ok1 ? l1 : l2);
+			fq_record_load(R, d, text, rr, bb, qq, ll, lane);
+			fq_record_store(R, d, text, rr, bb, qq, ll, lane);
+		}
 
 		// consensus of the adapter bases behind the insert, from the untrimmed reads (AnalysisWorker.cpp:279-290); -ec never edits them
 		if ((r.flags & SPG_F_INSERT) && r.status == 0)

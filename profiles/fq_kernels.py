@@ -69,3 +69,14 @@ for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ns"]):
                             "dram_write_bytes_per_pair": a["wr"] / n, "dram_gbs": gbs, "frac_of_measured_hbm": gbs / 6547.8}
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(res, open(os.path.join(ROOT, "gpurun_out", "fq_kernels.json"), "w"), indent=1)
+
+if os.environ.get("FQ_NCU_FULL"):  # one full capture each of the two copy kernels (raw and source pages as CSV under gpurun_out/)
+    import gzip
+    for k in ("fq_pack", "fq_out_write"):
+        rep = f"/tmp/ncu_{k}"
+        subprocess.run(["ncu", "--set", "full", "--clock-control", "none", "--import-source", "on", "-k", f"regex:{k}", "-c", "1", "-o", rep, "-f"] + cmd[cmd.index(cli):],
+                       capture_output=True, text=True)
+        raw = subprocess.run(["ncu", "-i", rep + ".ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        open(os.path.join(ROOT, "gpurun_out", f"ncu_{k}_raw.csv"), "w").write(raw)
+        src = subprocess.run(["ncu", "-i", rep + ".ncu-rep", "--page", "source", "--csv"], capture_output=True, text=True).stdout
+        gzip.open(os.path.join(ROOT, "gpurun_out", f"ncu_{k}_src.csv.gz"), "wt").write(src)
