@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--config-pool", type=int, default=3)
     ap.add_argument("--parity-pairs", type=int, default=1_000_000, help="pairs of every config checked against the CPU oracle after timing (0 = off)")
     ap.add_argument("--e2e-pairs", type=int, default=1_000_000, help="pairs per pinned slot for the end-to-end measurement")
+    ap.add_argument("--no-qual-tails", action="store_true", help="end to end without the slots' quality tails (SPG_OPT_QUAL_TAILS 0: the kernel fetches every trimming point over PCIe)")
     ap.add_argument("--e2e-slots", type=int, default=4)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--only", default="", help="profiling aid: measure just this config (C2..C5) device-resident and print its result")
@@ -394,6 +395,8 @@ def main():
     if not args.no_e2e:
         ns, n_e = args.e2e_slots, args.e2e_pairs
         eng = sp.Engine(sp.TrimmingParameters(**head["params"]), devices=(local_rank,), n_slots=ns, max_pairs=n_e, max_len=L0)
+        tails = not args.no_qual_tails
+        eng.set_option(sp.OPT_QUAL_TAILS, 1 if tails else 0)
         t, l1, l2 = pool[0]
         for s in range(ns):
             sl = eng.slot(s)
@@ -402,6 +405,8 @@ def main():
                 getattr(sl, k)[:n_e] = t[k][o : o + n_e].cpu().numpy()
             sl.len1[:n_e] = l1[o : o + n_e].cpu().numpy().view(np.uint16)
             sl.len2[:n_e] = l2[o : o + n_e].cpu().numpy().view(np.uint16)
+            if tails:
+                sl.fill_qtails(n_e)
 
         def e2e_step():
             for s in range(ns):
@@ -422,16 +427,36 @@ def main():
         total_launches += eng.launch_count - l0
         el = sharding.reduce_max(el, dist, dev)
         zero_copy = eng.zero_copy_quals
-        copied = ns * (n_e * (2 if zero_copy else 4) * stride0 + 2 * 2 * n_e)
+        copied = ns * (n_e * (2 if zero_copy else 4) * stride0 + 2 * 2 * n_e + (2 * sp.QTAIL * n_e if zero_copy and tails else 0))
+        # parity of the end-to-end path: the records the last step left in slot 0 against the oracle on the slot's own rows
+        e2e_parity = None
+        if rank == 0 and args.parity_pairs > 0:
+            sl = eng.slot(0)
+            npar = min(n_e, args.parity_pairs)
+            eng.submit(0, n_e)
+            got = eng.wait(0)[:npar].copy()
+            hb = H.Batch(npar, stride0)
+            for k in ("bases1", "quals1", "bases2", "quals2"):
+                getattr(hb, k)[:npar] = getattr(sl, k)[:npar]
+            hb.len1[:npar] = sl.len1[:npar]
+            hb.len2[:npar] = sl.len2[:npar]
+            want, _ = H.oracle_trim(hb, threads=host_threads(), **head["params"])
+            mism = int((got.view(np.uint64) != want.view(np.uint64)).sum())
+            e2e_parity = {"pairs": npar, "mismatches": mism}
+            assert mism == 0, f"end-to-end records differ from the oracle in {mism} of {npar} pairs"
         e2e = {"value": sharding.aggregate_throughput(e_steps * ns * n_e, world, el) / 1e6, "unit": UNIT, "h2d_bytes_per_step": copied,
                "d2h_bytes_per_step": ns * n_e * 8, "steps": e_steps, "pairs_per_step": ns * n_e, "kernel": eng.last_kernel,
                "h2d_copied_gbs_per_gpu": copied * e_steps / el / 1e9,
                "boundary": "spg_submit/spg_wait on pinned host SoA slots (ASCII rows as FASTQ delivers them), wall clock incl. H2D + kernel + D2H; the slots are filled once "
                            "and resubmitted every step (the E boundary of SURVEY.md 8d starts at the filled slot)",
                "host": host_topology()}
+        if e2e_parity:
+            e2e["parity"] = e2e_parity
         if zero_copy:
-            e2e["zero_copy"] = ("the two quality planes stay in the pinned slot: the kernel reads the sectors that hold the trimming points over PCIe itself "
-                                "(about two 32-byte sectors per read); h2d_bytes_per_step counts the copied planes (bases, lengths) only")
+            e2e["zero_copy"] = ("the two quality planes stay in the pinned slot: the kernel reads the sectors that hold the trimming points over PCIe itself; "
+                                "h2d_bytes_per_step counts what is copied (bases, lengths" + (", quality tails" if tails else "") + ")")
+            e2e["qual_tails"] = (f"SPG_OPT_QUAL_TAILS: the stager also writes the last {sp.QTAIL} qualities of every read into the slot (2 x {sp.QTAIL} B per pair, copied with the bases); "
+                                 "only reads cut by the adapter steps or trimmed deeper than 12 windows go to their quality row over PCIe") if tails else "off"
         eng.close()
 
     # ---- CPU baseline on a bounded sample of the same workload (rank 0, N=1 only)
@@ -526,6 +551,7 @@ def main():
             n_e = args.e2e_pairs
             ns = (4 if world <= 2 else 2) * world  # pinned slots of 1 M pairs each: 2 per device are enough to keep copies and kernels overlapped
             eng = sp.Engine(sp.TrimmingParameters(**c["params"]), devices=tuple(range(world)), n_slots=ns, max_pairs=n_e, max_len=L5)
+            eng.set_option(sp.OPT_QUAL_TAILS, 0 if args.no_qual_tails else 1)
             cfg = sp.SynthConfig(read_len=L5, **c["synth"])
             t, l1, l2 = alloc(n_e, s5)
             for s in range(ns):
@@ -536,6 +562,8 @@ def main():
                     getattr(sl, k)[:n_e] = t[k][:n_e].cpu().numpy()
                 sl.len1[:n_e] = l1[:n_e].cpu().numpy().view(np.uint16)
                 sl.len2[:n_e] = l2[:n_e].cpu().numpy().view(np.uint16)
+                if not args.no_qual_tails:
+                    sl.fill_qtails(n_e)
             # parity of the multi-device path: the records of slot ns-1 (device (ns-1) % N) against the oracle
             rounds = max(3, min(args.steps, 10))
             checks = []
@@ -577,10 +605,10 @@ def main():
                 checked += m
             assert mism == 0, f"round-robin engine: {mism} records differ from the oracle"
             zc = eng.zero_copy_quals
-            copied = n_e * (2 if zc else 4) * s5 + 2 * 2 * n_e
+            copied = n_e * (2 if zc else 4) * s5 + 2 * 2 * n_e + (2 * sp.QTAIL * n_e if zc and not args.no_qual_tails else 0)
             rr = {"value": rounds * ns * n_e / el / 1e6, "unit": UNIT, "workload": c["desc"], "devices": world, "slots": ns, "pairs_per_slot": n_e, "rounds": rounds,
                   "h2d_bytes_per_slot": copied, "h2d_copied_gbs_total": rounds * ns * copied / el / 1e9, "kernel": eng.last_kernel,
-                  "parity": {"pairs": checked, "mismatches": mism},
+                  "parity": {"pairs": checked, "mismatches": mism}, "qual_tails": not args.no_qual_tails,
                   "boundary": "ONE process, spg_create over all devices, slot s on device s % N, spg_submit ring with in-order spg_wait (what ThreadCoordinator::analyze becomes); "
                               "the other ranks idle on a host-side barrier",
                   "host": host_topology()}

@@ -138,6 +138,16 @@ int spg_create(spg_ctx** ctx, const spg_params* params, const int* device_ids, i
 /* Replaces: AnalysisJob storage (Auxilary.h:37-39). Pointers stay valid until spg_destroy. */
 int spg_slot_buffers(spg_ctx* ctx, int slot, spg_slot_view* view);
 
+/* Quality tails of a slot (optional, SPG_OPT_QUAL_TAILS): two more pinned planes of max_pairs x SPG_QTAIL bytes. Row r of qtail1 holds the
+   last SPG_QTAIL qualities of read 1 of pair r, i.e. quals1[r*stride + len1[r] - SPG_QTAIL + j] for j = 0 .. SPG_QTAIL-1 (a shorter read
+   right-aligned, the bytes in front of it are ignored); qtail2 likewise. The reference has no counterpart: FastqEntry::trimQuality
+   (src/cppNGS/FastqFileStream.cpp:52-87) walks the quality string from its 3' end, and for most reads the decision falls within the last
+   few bases. With the option set, spg_submit ships these 2 x 16 bytes per pair next to the bases while the quality rows stay in the
+   pinned slot; the kernel goes to a row only for reads that were cut by the adapter steps or whose trimming point lies further left.
+   The caller's stager writes the tails while it copies the quality string (GpuAnalysisWorker::start). */
+#define SPG_QTAIL 16
+int spg_slot_qtails(spg_ctx* ctx, int slot, uint8_t** qtail1, uint8_t** qtail2);
+
 /* Replaces: thread_pool_analyze_.start(worker) (ThreadCoordinator.cpp:97). Asynchronous: H2D copy of the first n_pairs
    rows, the trimming kernel, D2H of the results (and of the edited rows with -ec) are queued on the slot's device stream. */
 int spg_submit(spg_ctx* ctx, int slot, int n_pairs);
@@ -272,6 +282,8 @@ void spg_fq_close(spg_fq* fq);
 #define SPG_OPT_ZERO_COPY_QUALS 9 /* slots (spg_submit): 1 (default) = when the lane-per-pair kernel runs, the quality planes are not copied; the kernel reads
                                      the few quality bytes it needs from the pinned slot over PCIe. 0 = all four planes are copied */
 #define SPG_OPT_N_LANES 10        /* lane-per-pair kernel: 1 (default) = pairs with N take its N-aware path, 0 = the warp-cooperative general path */
+#define SPG_OPT_QUAL_TAILS 11     /* slots (spg_submit): 1 = the caller fills qtail1 / qtail2 of every slot it submits (spg_slot_qtails); they are copied with the
+                                     bases when the quality planes stay in the slot (SPG_OPT_ZERO_COPY_QUALS). 0 (default) = the tails are not looked at */
 int spg_set_option(spg_ctx* ctx, int option, int value);
 
 int spg_get_option(spg_ctx* ctx, int option, int* value);

@@ -238,7 +238,7 @@ enum SlotState
 struct Slot
 {
 	int dev = 0;
-	uint8_t* h_block = nullptr; // pinned: b1|q1|b2|q2|len1|len2
+	uint8_t* h_block = nullptr; // pinned: b1|q1|b2|q2|len1|len2|qtail1|qtail2
 	uint8_t* h_block_dev = nullptr; // the same memory as the slot's device sees it (mapped pinned memory)
 	bool zero_copy = false;     // last submit left the quality planes in the slot (see spg_submit)
 	uint8_t* d_block = nullptr;
@@ -267,7 +267,7 @@ struct spg_ctx
 	std::vector<Device> devs;
 	std::vector<Slot> slots;
 	int max_pairs = 0, max_len = 0, stride = 0;
-	size_t plane_bytes = 0, len_bytes = 0, block_bytes = 0;
+	size_t plane_bytes = 0, len_bytes = 0, tail_bytes = 0, block_bytes = 0; // slot block: b1|q1|b2|q2|len1|len2|qtail1|qtail2
 	std::string err;
 	std::mutex mu;
 	int force_bytewise = 0;
@@ -278,6 +278,7 @@ struct spg_ctx
 	int stages = 0;     // 0 = automatic
 	long long launches = 0;
 	int n_lanes = 1;                   // SPG_OPT_N_LANES: pairs with N go through the lane kernel's N-aware path (0: warp-cooperative general path)
+	int qual_tails = 0;                // SPG_OPT_QUAL_TAILS: the caller fills the slots' qtail1 / qtail2 (spg_slot_qtails)
 	int zero_copy_quals = 1;           // SPG_OPT_ZERO_COPY_QUALS: slots leave the quality planes in pinned host memory when the lane kernel runs
 	int seed_scan = 1;                 // SPG_OPT_SEED_SCAN: 0 = the lane kernel evaluates every offset of the adapter scans (no pigeonhole filter)
 	int kernel_layout = 0;             // SPG_OPT_KERNEL: 0 automatic, 1 warp per pair only, 2 lane per pair where it applies
@@ -440,7 +441,8 @@ int full_index(int nw, int full_len)
 // n_dev: optional device pointer to the actual pair count (<= n); n then sizes the grid only.
 // full_hint: read length most pairs of the batch are expected to have (0 = unknown); selects the kernel variant only.
 int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, uint8_t* q2, const uint16_t* len1, const uint16_t* len2, int stride, long long n,
-                spg_result* out, cudaStream_t stream, const int* n_dev = nullptr, int full_hint = -1, bool* lanes_query = nullptr, bool quals_on_host = false)
+                spg_result* out, cudaStream_t stream, const int* n_dev = nullptr, int full_hint = -1, bool* lanes_query = nullptr, bool quals_on_host = false,
+                const uint8_t* qt1 = nullptr, const uint8_t* qt2 = nullptr)
 {
 	// lanes_query: only answer whether this launch would run the lane-per-pair kernel (nothing is launched)
 	if (n <= 0 && !lanes_query) return SPG_OK;
@@ -451,6 +453,8 @@ int launch_trim(spg_ctx* ctx, Device& d, uint8_t* b1, uint8_t* q1, uint8_t* b2, 
 	memset(&a, 0, sizeof(a));
 	a.n_dev = n_dev;
 	a.quals_on_host = quals_on_host ? 1 : 0;
+	a.qt1 = qt1;
+	a.qt2 = qt2;
 	a.n_lanes = ctx->n_lanes;
 	a.b1 = b1;
 	a.q1 = q1;
@@ -769,7 +773,8 @@ int spg_create(spg_ctx** out, const spg_params* params, const int* device_ids, i
 	const int cap = (max_pairs + 7) / 8 * 8;
 	ctx->plane_bytes = (size_t)cap * ctx->stride;
 	ctx->len_bytes = (size_t)cap * sizeof(uint16_t);
-	ctx->block_bytes = 4 * ctx->plane_bytes + 2 * ctx->len_bytes;
+	ctx->tail_bytes = (size_t)cap * SPG_QTAIL;
+	ctx->block_bytes = 4 * ctx->plane_bytes + 2 * ctx->len_bytes + 2 * ctx->tail_bytes;
 
 #define CREATE_CUDA(call)                                                                     \
 	do                                                                                        \
@@ -845,6 +850,16 @@ int spg_slot_buffers(spg_ctx* ctx, int slot, spg_slot_view* v)
 	return SPG_OK;
 }
 
+int spg_slot_qtails(spg_ctx* ctx, int slot, uint8_t** qtail1, uint8_t** qtail2)
+{
+	if (!ctx || !qtail1 || !qtail2) return SPG_ERR_PARAM;
+	if (slot < 0 || slot >= (int)ctx->slots.size()) return fail(ctx, SPG_ERR_PARAM, "slot out of range");
+	Slot& sl = ctx->slots[(size_t)slot];
+	*qtail1 = sl.h_block + 4 * ctx->plane_bytes + 2 * ctx->len_bytes;
+	*qtail2 = *qtail1 + ctx->tail_bytes;
+	return SPG_OK;
+}
+
 int spg_submit(spg_ctx* ctx, int slot, int n_pairs)
 {
 	if (!ctx) return SPG_ERR_PARAM;
@@ -871,12 +886,27 @@ int spg_submit(spg_ctx* ctx, int slot, int n_pairs)
 			if (qrc != SPG_OK) return qrc;
 		}
 		sl.zero_copy = zero_copy;
+		const bool tails = zero_copy && ctx->qual_tails;
 		if (zero_copy)
 		{
 			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block, sl.h_block, rows, cudaMemcpyHostToDevice, sl.stream));
 			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 2 * pb, sl.h_block + 2 * pb, rows, cudaMemcpyHostToDevice, sl.stream));
-			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb, sl.h_block + 4 * pb, lens, cudaMemcpyHostToDevice, sl.stream));
-			SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb + ctx->len_bytes, sl.h_block + 4 * pb + ctx->len_bytes, lens, cudaMemcpyHostToDevice, sl.stream));
+			const size_t lb = ctx->len_bytes, tb = ctx->tail_bytes;
+			if (2 * (size_t)n_pairs >= (size_t)ctx->max_pairs) // lengths [and tails] of a well-filled slot in one copy (they lie side by side)
+			{
+				SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb, sl.h_block + 4 * pb, 2 * lb + (tails ? 2 * tb : 0), cudaMemcpyHostToDevice, sl.stream));
+			}
+			else
+			{
+				SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb, sl.h_block + 4 * pb, lens, cudaMemcpyHostToDevice, sl.stream));
+				SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb + lb, sl.h_block + 4 * pb + lb, lens, cudaMemcpyHostToDevice, sl.stream));
+				if (tails)
+				{
+					const size_t tn = (size_t)n_pairs * SPG_QTAIL;
+					SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb + 2 * lb, sl.h_block + 4 * pb + 2 * lb, tn, cudaMemcpyHostToDevice, sl.stream));
+					SPG_CUDA(ctx, cudaMemcpyAsync(sl.d_block + 4 * pb + 2 * lb + tb, sl.h_block + 4 * pb + 2 * lb + tb, tn, cudaMemcpyHostToDevice, sl.stream));
+				}
+			}
 		}
 		else if (n_pairs == ctx->max_pairs)
 		{
@@ -897,7 +927,8 @@ int spg_submit(spg_ctx* ctx, int slot, int n_pairs)
 		uint8_t* const q1 = zero_copy ? sl.h_block_dev + pb : sl.d_block + pb;
 		uint8_t* const q2 = zero_copy ? sl.h_block_dev + 3 * pb : sl.d_block + 3 * pb;
 		int rc = launch_trim(ctx, d, sl.d_block, q1, sl.d_block + 2 * pb, q2, reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb),
-		                     reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.d_res, sl.stream, nullptr, -1, nullptr, zero_copy);
+		                     reinterpret_cast<const uint16_t*>(sl.d_block + 4 * pb + ctx->len_bytes), ctx->stride, n_pairs, sl.d_res, sl.stream, nullptr, -1, nullptr, zero_copy,
+		                     tails ? sl.d_block + 4 * pb + 2 * ctx->len_bytes : nullptr, tails ? sl.d_block + 4 * pb + 2 * ctx->len_bytes + ctx->tail_bytes : nullptr);
 		if (rc != SPG_OK) return rc;
 		SPG_CUDA(ctx, cudaMemcpyAsync(sl.h_res, sl.d_res, (size_t)n_pairs * sizeof(spg_result), cudaMemcpyDeviceToHost, sl.stream));
 		if (ctx->params.ec) // edited rows come back in the slot
@@ -1064,6 +1095,7 @@ int spg_set_option(spg_ctx* ctx, int option, int value)
 		case SPG_OPT_SEED_SCAN: ctx->seed_scan = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_ZERO_COPY_QUALS: ctx->zero_copy_quals = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_N_LANES: ctx->n_lanes = value ? 1 : 0; return SPG_OK;
+		case SPG_OPT_QUAL_TAILS: ctx->qual_tails = value ? 1 : 0; return SPG_OK;
 		case SPG_OPT_KERNEL:
 			if (value < 0 || value > 2) return fail(ctx, SPG_ERR_PARAM, "kernel layout must be 0 (automatic), 1 (warp per pair) or 2 (lane per pair)");
 			ctx->kernel_layout = value;
@@ -1109,6 +1141,7 @@ int spg_get_option(spg_ctx* ctx, int option, int* value)
 		case SPG_OPT_SEED_SCAN: *value = ctx->seed_scan; return SPG_OK;
 		case SPG_OPT_ZERO_COPY_QUALS: *value = ctx->zero_copy_quals; return SPG_OK;
 		case SPG_OPT_N_LANES: *value = ctx->n_lanes; return SPG_OK;
+		case SPG_OPT_QUAL_TAILS: *value = ctx->qual_tails; return SPG_OK;
 		default: return fail(ctx, SPG_ERR_PARAM, "unknown option");
 	}
 }

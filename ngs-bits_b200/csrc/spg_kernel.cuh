@@ -76,6 +76,8 @@ struct KArgs
 	int a1maxmm, a2maxmm;    // the same as a limit: most mismatches with which a full window passes (-1: never); only valid if full_ok
 	int full_ok;             // adapters without N in their first a_size bases and every pass set of steps 2/3 an interval 0..k of mismatches
 	int quals_on_host;       // lane kernel: q1 / q2 point into mapped pinned host memory (zero copy): no speculative prefetches over PCIe
+	const uint8_t* qt1;      // lane kernel, or null: [n][16] the last 16 qualities of every read 1 (positions len-16 .. len-1), device memory
+	const uint8_t* qt2;
 	int n_lanes;             // lane kernel: pairs with N take the N-aware lane path (0: the general path, SPG_OPT_N_LANES)
 	int seed_n1_ok;          // lane kernel: the same for a full window that holds one N (a_size-1 compared bases, one block lost)
 	int seed_ok;             // lane kernel: every passing window of steps 2/3 has fewer mismatches than complete 4-base adapter blocks (and full_ok)

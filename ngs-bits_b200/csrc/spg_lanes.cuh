@@ -487,6 +487,7 @@ __device__ __forceinline__ int lane_last_good(const uint8_t* qrow, int n, int cu
 
 // windows of 5 starting at lo .. e-5 (lo <= e-5 is not required), bytes [lo, lo+16) of the row. Returns the new length if one of them
 // passes (highest start first, then the trailing bases below the cutoff are dropped), -1 if none does, -2 for a byte >= 0x80.
+__device__ __forceinline__ int lane_quality5_eval(const uint32_t (&v)[4], int lo, int e, int cutb, int thrb); // v: the 16 bytes [lo, lo+16)
 __device__ __forceinline__ int lane_quality5_block(const uint8_t* qrow, int lo, int e, int cutb, int thrb)
 {
 	// two aligned 16-byte loads cover the 16 bytes wherever they start; the second one is not needed for an aligned start
@@ -509,6 +510,10 @@ __device__ __forceinline__ int lane_quality5_block(const uint8_t* qrow, int lo, 
 	uint32_t v[4];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) v[k] = __funnelshift_r(w[k], w[k + 1], 8u * boff); // bytes of positions lo+4k ..
+	return lane_quality5_eval(v, lo, e, cutb, thrb);
+}
+__device__ __forceinline__ int lane_quality5_eval(const uint32_t (&v)[4], int lo, int e, int cutb, int thrb)
+{
 	if ((v[0] | v[1] | v[2] | v[3]) & 0x80808080u) return -2;
 	const uint32_t ge = lane_ge16(v, cutb); // bit j: quality of position lo+j reaches the cutoff
 	auto byte_at = [&](int j) -> int { return (int)prmt(v[j >> 2], 0u, 0x4440u | (uint32_t)(j & 3)); };
@@ -557,6 +562,25 @@ __device__ __forceinline__ int lane_trim_quality5(const KArgs& A, const uint8_t*
 		if (lo == 0) return 0;
 		e = lo + 4;
 	}
+}
+
+// The same with the read's last 16 qualities at hand (`qtail`, device memory, or null; SPG_OPT_QUAL_TAILS: the caller ships them with
+// the bases while the quality rows stay in the pinned slot). A read that the adapter steps left alone (n == len >= 16) is decided from
+// them whenever one of the twelve windows at its 3' end passes -- most reads; every other read goes to its quality row as before.
+__device__ __forceinline__ int lane_trim_quality5_tail(const KArgs& A, const uint8_t* qtail, const uint8_t* qrow, int n, int len)
+{
+	if (qtail != nullptr && n == len && n >= 16)
+	{
+		const int cutb = A.qcut + A.qoff, thrb = A.qthr + 5 * A.qoff;
+		if (cutb >= 1 && cutb <= 127)
+		{
+			const uint4 c = __ldg(reinterpret_cast<const uint4*>(qtail));
+			const uint32_t v[4] = {c.x, c.y, c.z, c.w};
+			const int r = lane_quality5_eval(v, n - 16, n, cutb, thrb);
+			if (r >= 0) return r; // -1 (no window of the twelve passes) and -2 (a byte >= 0x80): the search in the row decides
+		}
+	}
+	return lane_trim_quality5(A, qrow, n);
 }
 
 // General search: any window <= 8, any trimming point.
@@ -689,8 +713,8 @@ __device__ __forceinline__ void lane_finish(const KArgs& A, uint32_t p, bool pla
 		int t1 = -2, t2 = -2; // -2: not decided yet
 		if (A.qwin == 5 && plain)
 		{
-			t1 = lane_trim_quality5(A, A.q1 + goff, n1);
-			t2 = lane_trim_quality5(A, A.q2 + goff, n2);
+			t1 = lane_trim_quality5_tail(A, A.qt1 ? A.qt1 + 16 * (size_t)p : nullptr, A.q1 + goff, n1, FULL);
+			t2 = lane_trim_quality5_tail(A, A.qt2 ? A.qt2 + 16 * (size_t)p : nullptr, A.q2 + goff, n2, FULL);
 		}
 		if (__any_sync(kFull, plain && t1 < 0)) t1 = lane_trim_quality(A, A.q1 + goff, n1, plain && t1 < 0, scr, t1);
 		if (__any_sync(kFull, plain && t2 < 0)) t2 = lane_trim_quality(A, A.q2 + goff, n2, plain && t2 < 0, scr, t2);

@@ -57,6 +57,17 @@ void GpuAnalysisWorker::start()
 	spg_slot_view v;
 	if (spg_slot_buffers(engine_, slot_, &v) != SPG_OK) throw Exception(spg_last_error(engine_));
 	if (job_.read_count > v.max_pairs) throw ProgrammingException("job is larger than the engine slot");
+	// the last SPG_QTAIL qualities of every read go into the slot's tail planes as well (SPG_OPT_QUAL_TAILS, set by the command line): they
+	// travel with the bases, the quality rows stay in the pinned slot
+	uint8_t* qt1 = nullptr;
+	uint8_t* qt2 = nullptr;
+	int tails = 0;
+	if (spg_get_option(engine_, SPG_OPT_QUAL_TAILS, &tails) != SPG_OK) throw Exception(spg_last_error(engine_));
+	if (tails && spg_slot_qtails(engine_, slot_, &qt1, &qt2) != SPG_OK) throw Exception(spg_last_error(engine_));
+	auto writeTail = [](uint8_t* tail, const std::string& q) {
+		const size_t n = std::min(q.size(), (size_t)SPG_QTAIL);
+		memcpy(tail + SPG_QTAIL - n, q.data() + q.size() - n, n);
+	};
 
 	for (int r = 0; r < job_.read_count; ++r)
 	{
@@ -91,6 +102,11 @@ void GpuAnalysisWorker::start()
 		memcpy(v.quals2 + off, e2.qualities.data(), len2);
 		v.len1[r] = (uint16_t)len1;
 		v.len2[r] = (uint16_t)len2;
+		if (tails)
+		{
+			writeTail(qt1 + (size_t)r * SPG_QTAIL, e1.qualities);
+			writeTail(qt2 + (size_t)r * SPG_QTAIL, e2.qualities);
+		}
 		job_.length_r1_orig[(size_t)r] = (int)len1;
 		job_.length_r2_orig[(size_t)r] = (int)len2;
 	}

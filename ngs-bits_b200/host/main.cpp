@@ -301,6 +301,7 @@ int main(int argc, char** argv)
 			}
 			if (spg_create(&engine, &ep, params.gpus.data(), (int)params.gpus.size(), n_jobs, params.block_size, max_len) != SPG_OK)
 				throw Exception(std::string("Could not initialize the CUDA trimming engine: ") + spg_last_error(nullptr));
+			spg_set_option(engine, SPG_OPT_QUAL_TAILS, 1); // GpuAnalysisWorker::start writes the slots' quality tails
 			engine_max_len = max_len;
 		};
 

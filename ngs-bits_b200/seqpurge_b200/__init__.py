@@ -19,7 +19,8 @@ LIB_PATH = os.environ.get("SPG_LIB") or os.path.join(os.path.dirname(_HERE), "li
 MAXLEN = 1000
 F_INSERT, F_ADAPTER, F_Q1, F_Q2, F_N1, F_N2 = 1, 2, 4, 8, 16, 32
 PAIR_OK, PAIR_BAD_BASE_R2, PAIR_TOO_LONG, PAIR_BAD_BASE_EC = 0, 1, 2, 3
-OPT_FORCE_BYTEWISE, OPT_GRID_CTAS_PER_SM, OPT_MIN_BLOCKS, OPT_TILE_PAIRS, OPT_STAGES, OPT_FULL_LEN, OPT_KERNEL, OPT_SEED_SCAN, OPT_ZERO_COPY_QUALS, OPT_N_LANES = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
+OPT_FORCE_BYTEWISE, OPT_GRID_CTAS_PER_SM, OPT_MIN_BLOCKS, OPT_TILE_PAIRS, OPT_STAGES, OPT_FULL_LEN, OPT_KERNEL, OPT_SEED_SCAN, OPT_ZERO_COPY_QUALS, OPT_N_LANES, OPT_QUAL_TAILS = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
+QTAIL = 16  # SPG_QTAIL
 KERNEL_AUTO, KERNEL_WARP_PER_PAIR, KERNEL_LANE_PER_PAIR = 0, 1, 2
 
 RESULT_DTYPE = np.dtype([("len1", "<u2"), ("len2", "<u2"), ("best_offset", "<i2"), ("flags", "u1"), ("status", "u1")])
@@ -94,6 +95,8 @@ _lib.spg_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(_Params), C.POINTER
 _lib.spg_create.restype = C.c_int
 _lib.spg_slot_buffers.argtypes = [C.c_void_p, C.c_int, C.POINTER(_SlotView)]
 _lib.spg_slot_buffers.restype = C.c_int
+_lib.spg_slot_qtails.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+_lib.spg_slot_qtails.restype = C.c_int
 _lib.spg_submit.argtypes = [C.c_void_p, C.c_int, C.c_int]
 _lib.spg_submit.restype = C.c_int
 _lib.spg_wait.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -176,8 +179,11 @@ def _np_view(ptr, shape, dtype):
 class Slot:
     """Pinned host SoA of one job (one AnalysisJob of the reference's pool)."""
 
-    def __init__(self, view):
+    def __init__(self, view, qtail1=None, qtail2=None):
         self.stride, self.max_pairs = view.stride, view.max_pairs
+        if qtail1:  # the optional quality tails (spg_slot_qtails, OPT_QUAL_TAILS)
+            self.qtail1 = _np_view(qtail1, (view.max_pairs, QTAIL), np.uint8)
+            self.qtail2 = _np_view(qtail2, (view.max_pairs, QTAIL), np.uint8)
         shp = (view.max_pairs, view.stride)
         self.bases1 = _np_view(view.bases1, shp, np.uint8)
         self.quals1 = _np_view(view.quals1, shp, np.uint8)
@@ -185,6 +191,16 @@ class Slot:
         self.quals2 = _np_view(view.quals2, shp, np.uint8)
         self.len1 = _np_view(view.len1, (view.max_pairs,), np.uint16)
         self.len2 = _np_view(view.len2, (view.max_pairs,), np.uint16)
+
+    def fill_qtails(self, n):
+        """Writes the last QTAIL qualities of the first n reads of both planes into qtail1 / qtail2 (what a stager does while it copies a
+        read's quality string; shorter reads right-aligned). Vectorised for tests and bench.py."""
+        cols = np.arange(QTAIL, dtype=np.int64)[None, :]
+        for q, ln, qt in ((self.quals1, self.len1, self.qtail1), (self.quals2, self.len2, self.qtail2)):
+            idx = ln[:n].astype(np.int64)[:, None] - QTAIL + cols  # position of tail byte j in its row (negative: in front of the read)
+            ok = idx >= 0
+            rows = np.arange(n, dtype=np.int64)[:, None]
+            qt[:n] = np.where(ok, q[:n][rows, np.where(ok, idx, 0)], 0)
 
 
 class _FqConfig(C.Structure):
@@ -247,7 +263,9 @@ class Engine:
         if i not in self._slots:
             v = _SlotView()
             self._check(_lib.spg_slot_buffers(self._h, i, C.byref(v)), "spg_slot_buffers")
-            self._slots[i] = Slot(v)
+            t1, t2 = C.c_void_p(), C.c_void_p()
+            self._check(_lib.spg_slot_qtails(self._h, i, C.byref(t1), C.byref(t2)), "spg_slot_qtails")
+            self._slots[i] = Slot(v, t1.value, t2.value)
         return self._slots[i]
 
     def submit(self, slot, n_pairs):

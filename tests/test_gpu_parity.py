@@ -29,7 +29,7 @@ def sp():
     return seqpurge_b200
 
 
-def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=None, kernel=None, expect_kernel=None, seed_scan=None, **params):
+def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=None, kernel=None, expect_kernel=None, seed_scan=None, qual_tails=False, **params):
     """Run a Batch through spg_submit/spg_wait (pinned slot, H2D, kernel, D2H). Returns records (+ edited batch, ec stats with ec)."""
     p = sp.TrimmingParameters(**params)
     chunk = chunk or batch.n
@@ -42,6 +42,8 @@ def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=No
         eng.set_option(sp.OPT_KERNEL, kernel)
     if seed_scan is not None:  # lane-per-pair kernel: exact-block filter in front of the adapter scans on / off
         eng.set_option(sp.OPT_SEED_SCAN, seed_scan)
+    if qual_tails:  # the stager also fills the slots' quality tails (spg_slot_qtails): they are shipped instead of the quality planes
+        eng.set_option(sp.OPT_QUAL_TAILS, 1)
     out = np.zeros(batch.n, sp.RESULT_DTYPE)
     edited = batch.copy() if params.get("ec") else None
     starts = list(range(0, batch.n, chunk))
@@ -60,6 +62,8 @@ def gpu_trim(sp, batch, force_bytewise=False, n_slots=1, chunk=None, full_len=No
             getattr(s, name)[:n] = getattr(batch, name)[st : st + n]
         s.len1[:n] = batch.len1[st : st + n]
         s.len2[:n] = batch.len2[st : st + n]
+        if qual_tails:
+            s.fill_qtails(n)
         eng.submit(slot, n)
         inflight.append((slot, st, n))
     for s0, st0, n0 in inflight:
@@ -475,6 +479,49 @@ def test_lane_per_pair_kernel(sp, name):
     assert_same(every, want, batch)
     warp, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_WARP_PER_PAIR, expect_kernel="trim_kernel", **params)
     assert_same(warp, want, batch)
+    tails, _, _ = gpu_trim(sp, batch, full_len=L, kernel=sp.KERNEL_LANE_PER_PAIR, qual_tails=True, **params)  # quality tails shipped with the bases
+    assert_same(tails, want, batch)
+
+
+def test_quality_tails_in_the_slot(sp):
+    """SPG_OPT_QUAL_TAILS: the last 16 qualities of every read travel with the bases, the quality rows stay in the pinned slot. Reads whose
+    trimming point lies within the tail are decided from it, all others (cut by the adapter steps, trimmed deeper, bytes >= 0x80 in the
+    tail, shorter than the row) from the row -- the records must not depend on the option. Slots filled to less than half take the
+    separate copies of spg_submit, the last tile is ragged, rows start in the middle of a word."""
+    L = 150
+    batch = H.random_batch(32 * 20 + 5, L, seed=77, stride=L, insert_mean=170, insert_sd=80, error_rate=0.02, n_rate=0.001, lowq_tail=9.0)
+    rng = np.random.default_rng(3)
+    for i in rng.choice(batch.n, 60, replace=False):  # qualities the byte arithmetic of the fast search does not cover
+        batch.quals1[i, L - 1 - int(rng.integers(0, 16))] = 0x80 + int(rng.integers(0, 100))
+    for i in rng.choice(batch.n, 60, replace=False):  # tails that fail completely: the search goes on in the row
+        batch.quals2[i, L - 30 :] = 33 + 2
+    r = H.random_batch(100, L, seed=10, ragged=True, stride=L)
+    for j in range(100):
+        for k in ("bases1", "quals1", "bases2", "quals2", "len1", "len2"):
+            getattr(batch, k)[6 * j + 2] = getattr(r, k)[j]
+    for params in (dict(), dict(qcut=25), dict(qcut=2), dict(qwin=7, qcut=20), dict(qcut=0)):
+        want, _ = H.oracle_trim(batch, **params)
+        for chunk, n_slots in ((None, 1), (300, 2)):
+            got, _, _ = gpu_trim(sp, batch, full_len=L, qual_tails=True, chunk=chunk, n_slots=n_slots, **params)
+            assert_same(got, want, batch)
+    # garbage in the tails of reads that are NOT decided from them must not matter: pairs with an insert hit are cut before quality trimming
+    want, _ = H.oracle_trim(batch)
+    p = sp.TrimmingParameters()
+    eng = sp.Engine(p, devices=(0,), n_slots=1, max_pairs=batch.n, max_len=L)
+    eng.set_option(sp.OPT_QUAL_TAILS, 1)
+    s = eng.slot(0)
+    for name in ("bases1", "quals1", "bases2", "quals2"):
+        getattr(s, name)[: batch.n] = getattr(batch, name)[: batch.n]
+    s.len1[: batch.n] = batch.len1[: batch.n]
+    s.len2[: batch.n] = batch.len2[: batch.n]
+    s.fill_qtails(batch.n)
+    hit = (want["flags"] & 1) != 0
+    assert hit.sum() > 50
+    s.qtail1[: batch.n][hit] = 33 + 40
+    s.qtail2[: batch.n][hit] = 33
+    eng.submit(0, batch.n)
+    assert_same(eng.wait(0).copy(), want, batch)
+    eng.close()
 
 
 def test_lane_per_pair_low_complexity_reads(sp):
