@@ -10,7 +10,10 @@
 // Blocks are dealt to the GPUs round robin (slot s -> device s % n) and retired in submission order, so the output equals the
 // reference's `-threads 1` output whatever the number of GPUs. -threads N (N > 1) deflates the output with N threads (same content,
 // other .gz bytes). -qc writes the read statistics as qcML (values only, no plots). Not supported here: -debug, -progress.
+#include <algorithm>
+#include <cerrno>
 #include <chrono>
+#include <climits>
 #include <condition_variable>
 #include <exception>
 #include <functional>
@@ -138,7 +141,14 @@ std::vector<int> parseIntList(const std::string& s)
 	std::vector<int> v;
 	std::stringstream ss(s);
 	std::string tok;
-	while (std::getline(ss, tok, ',')) v.push_back(atoi(tok.c_str()));
+	while (std::getline(ss, tok, ','))
+	{
+		char* end = nullptr;
+		const long x = strtol(tok.c_str(), &end, 10);
+		if (tok.empty() || *end != '\0' || x < 0 || x > 1023) throw CommandLineParsingException("'" + tok + "' in the device list '" + s + "' is not a CUDA device index!");
+		if (std::find(v.begin(), v.end(), (int)x) != v.end()) throw CommandLineParsingException("Device " + tok + " is listed twice in '" + s + "'!");
+		v.push_back((int)x);
+	}
 	return v;
 }
 
@@ -169,6 +179,30 @@ int main(int argc, char** argv)
 				if (i + 1 >= argc) throw CommandLineParsingException("Parameter '" + f + "' needs a value!");
 				return argv[++i];
 			};
+			// numbers like ToolBase parses them (QString::toInt / toDouble with an ok flag): anything that is not a number is an error
+			auto nextInt = [&]() -> int {
+				const std::string v = next();
+				char* end = nullptr;
+				errno = 0;
+				const long x = strtol(v.c_str(), &end, 10);
+				if (v.empty() || *end != '\0' || errno != 0 || x < INT_MIN || x > INT_MAX)
+					throw CommandLineParsingException("Value '" + v + "' of parameter '" + f + "' is not an integer!");
+				return (int)x;
+			};
+			auto nextDouble = [&]() -> double {
+				const std::string v = next();
+				char* end = nullptr;
+				errno = 0;
+				const double x = strtod(v.c_str(), &end);
+				if (v.empty() || *end != '\0' || errno != 0) throw CommandLineParsingException("Value '" + v + "' of parameter '" + f + "' is not a number!");
+				return x;
+			};
+			auto trimmed = [](std::string v) { // QByteArray::trimmed(), src/SeqPurge/main.cpp:67-69
+				const char* ws = " \t\n\v\f\r";
+				const size_t a = v.find_first_not_of(ws);
+				if (a == std::string::npos) return std::string();
+				return v.substr(a, v.find_last_not_of(ws) - a + 1);
+			};
 			auto list = [&](std::vector<std::string>& dst) {
 				while (i + 1 < argc && argv[i + 1][0] != '-') dst.push_back(argv[++i]);
 			};
@@ -183,26 +217,25 @@ int main(int argc, char** argv)
 			else if (f == "-out2") params.out2 = next();
 			else if (f == "-out3") params.out3 = next();
 			else if (f == "-summary") params.summary = next();
-			else if (f == "-a1") params.a1 = next();
-			else if (f == "-a2") params.a2 = next();
-			else if (f == "-match_perc") params.match_perc = atof(next().c_str());
-			else if (f == "-mep") params.mep = atof(next().c_str());
-			else if (f == "-qcut") params.qcut = atoi(next().c_str());
-			else if (f == "-qwin") params.qwin = atoi(next().c_str());
-			else if (f == "-qoff") params.qoff = atoi(next().c_str());
-			else if (f == "-ncut") params.ncut = atoi(next().c_str());
-			else if (f == "-min_len") params.min_len = atoi(next().c_str());
-			else if (f == "-threads") params.threads = atoi(next().c_str());
-			else if (f == "-block_size") params.block_size = atoi(next().c_str());
-			else if (f == "-block_prefetch") params.block_prefetch = atoi(next().c_str());
-			else if (f == "-progress") params.progress = atoi(next().c_str());
-			else if (f == "-compression_level") params.compression_level = atoi(next().c_str());
+			else if (f == "-a1") params.a1 = trimmed(next());
+			else if (f == "-a2") params.a2 = trimmed(next());
+			else if (f == "-match_perc") params.match_perc = nextDouble();
+			else if (f == "-mep") params.mep = nextDouble();
+			else if (f == "-qcut") params.qcut = nextInt();
+			else if (f == "-qwin") params.qwin = nextInt();
+			else if (f == "-qoff") params.qoff = nextInt();
+			else if (f == "-ncut") params.ncut = nextInt();
+			else if (f == "-min_len") params.min_len = nextInt();
+			else if (f == "-threads") params.threads = nextInt();
+			else if (f == "-block_size") params.block_size = nextInt();
+			else if (f == "-block_prefetch") params.block_prefetch = nextInt();
+			else if (f == "-compression_level") params.compression_level = nextInt();
 			else if (f == "-ec") params.ec = true;
 			else if (f == "-gpus") params.gpus = parseIntList(next());
 			else if (f == "-qc") params.qc = next();
 			else if (f == "-host_framing") params.host_framing = true;
 			else if (f == "-bgzf") params.bgzf = true;
-			else if (f == "-debug") throw CommandLineParsingException("Parameter '" + f + "' is not supported by seqpurge_b200.");
+			else if (f == "-debug" || f == "-progress") throw CommandLineParsingException("Parameter '" + f + "' is not supported by seqpurge_b200.");
 			else throw CommandLineParsingException("Unknown parameter '" + f + "'!");
 		}
 		if (params.files_in1.empty() || params.files_in2.empty() || params.out1.empty() || params.out2.empty())

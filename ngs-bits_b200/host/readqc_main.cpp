@@ -282,4 +282,9 @@ int main(int argc, char** argv)
 		std::cerr << e.what() << std::endl;
 		return 1;
 	}
+	catch (const std::exception& e) // std::bad_alloc, std::system_error of a thread that could not be started, ...
+	{
+		std::cerr << "Error: " << e.what() << std::endl;
+		return 1;
+	}
 }

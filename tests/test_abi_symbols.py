@@ -104,3 +104,10 @@ def test_command_lines_fail_loudly_without_a_gpu(lib, tmp_path):
         if not torch.cuda.is_available():
             r = subprocess.run([exe] + run_args, capture_output=True, text=True)
             assert r.returncode == 1 and "CUDA" in r.stderr, (tool, r.stderr)
+    # numbers are parsed strictly like ToolBase does (no silent 0 for '-qcut abc'), device lists must name each device once, adapters are trimmed
+    exe = os.path.join(bin_dir, "seqpurge_b200")
+    base = ["-in1", str(fq), "-in2", str(fq), "-out1", str(tmp_path / "a.gz"), "-out2", str(tmp_path / "b.gz")]
+    for extra, msg in ((["-qcut", "abc"], "is not an integer"), (["-mep", "1e-6x"], "is not a number"), (["-gpus", "0,0"], "listed twice"), (["-gpus", "-1"], "not a CUDA device index"),
+                       (["-progress", "100"], "not supported"), (["-a1", "  ACGT  "], "too short")):
+        r = subprocess.run([exe] + base + extra, capture_output=True, text=True)
+        assert r.returncode == 1 and msg in r.stderr, (extra, r.stderr)
