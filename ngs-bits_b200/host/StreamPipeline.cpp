@@ -84,6 +84,20 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 	const int n_slots = std::max(2, std::min(params.block_prefetch, 4)) * (int)params.gpus.size(); // chunks in flight: the GPU part of a chunk is far shorter than its inflate
 	(void)summary;
 
+	// The engine comes up first (CUDA context, decision tables: 0.3-1.5 s depending on the box). Started next to a pool of inflating threads it
+	// took 1.2-3.0 s on one box (profiles/cli_throughput_r2.log): context creation maps memory all the time and competes with the page
+	// faults of the readers for the address-space lock; the overlap it would buy is the inflate of one chunk.
+	spg_params ep = toEngineParams(params);
+	spg_ctx* engine = nullptr;
+	if (spg_create(&engine, &ep, params.gpus.data(), (int)params.gpus.size(), 0, 0, 0) != SPG_OK)
+		throw Exception(std::string("Could not initialize the CUDA trimming engine: ") + spg_last_error(nullptr));
+	struct EngineGuard
+	{
+		spg_ctx* e;
+		~EngineGuard() { spg_destroy(e); }
+	} engine_guard{engine};
+	t_init += since(tp);
+
 	std::unique_ptr<WorkerPool> pool;
 	if (params.threads > 1) pool.reset(new WorkerPool(params.threads));
 	std::unique_ptr<GzipTextWriter> writers[4];
@@ -111,19 +125,6 @@ void runStreamPipeline(const TrimmingParameters& params, std::ostream& summary, 
 		}
 	} reader_guard{q1, q2, reader1, reader2};
 
-	// the engine comes up (CUDA context, decision tables) while the readers already inflate
-	spg_params ep = toEngineParams(params);
-	spg_ctx* engine = nullptr;
-	if (spg_create(&engine, &ep, params.gpus.data(), (int)params.gpus.size(), 0, 0, 0) != SPG_OK)
-		throw Exception(std::string("Could not initialize the CUDA trimming engine: ") + spg_last_error(nullptr));
-	struct EngineGuard
-	{
-		spg_ctx* e;
-		~EngineGuard() { spg_destroy(e); }
-	} engine_guard{engine};
-
-
-	t_init += since(tp);
 
 	spg_fq* fq = nullptr;
 	int fq_max_len = 0;
