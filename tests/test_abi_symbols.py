@@ -111,3 +111,29 @@ def test_command_lines_fail_loudly_without_a_gpu(lib, tmp_path):
                        (["-progress", "100"], "not supported"), (["-a1", "  ACGT  "], "too short")):
         r = subprocess.run([exe] + base + extra, capture_output=True, text=True)
         assert r.returncode == 1 and msg in r.stderr, (extra, r.stderr)
+
+
+def test_slot_quality_tails_helper(lib):
+    """Slot.fill_qtails (what a stager does for SPG_OPT_QUAL_TAILS): row r of a tail plane = the last 16 qualities of read r, a shorter
+    read right-aligned. Checked against a direct loop on a slot made of plain numpy arrays (no device needed)."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "ngs-bits_b200"))
+    import seqpurge_b200 as sp  # the ctypes binding (loads the library `lib` built; needs no device for this)
+
+    s = sp.Slot.__new__(sp.Slot)
+    n, stride = 64, 40
+    rng = np.random.default_rng(1)
+    s.quals1 = rng.integers(33, 74, (n, stride)).astype(np.uint8)
+    s.quals2 = rng.integers(33, 74, (n, stride)).astype(np.uint8)
+    s.len1 = rng.integers(0, stride + 1, n).astype(np.uint16)
+    s.len2 = rng.integers(0, stride + 1, n).astype(np.uint16)
+    s.len1[:3] = (0, 16, stride)
+    s.qtail1 = np.full((n, sp.QTAIL), 255, np.uint8)
+    s.qtail2 = np.full((n, sp.QTAIL), 255, np.uint8)
+    s.fill_qtails(n)
+    for q, ln, qt in ((s.quals1, s.len1, s.qtail1), (s.quals2, s.len2, s.qtail2)):
+        for i in range(n):
+            L = int(ln[i])
+            k = min(L, sp.QTAIL)
+            assert (qt[i, sp.QTAIL - k :] == q[i, L - k : L]).all(), i
